@@ -1,0 +1,57 @@
+// Internal interface between the C ABI (st_abi.cu) and the kernels (st_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace st {
+
+enum Mode : int { MODE_STEP = 0, MODE_RESET = 1, MODE_OBSERVE = 2 };
+
+constexpr int kWarpsPerCta = 8;       // one env per warp, 8 envs per CTA pass
+constexpr int kThreads = 32 * kWarpsPerCta;
+constexpr int kImage = 84;            // ref:426: _observation always renders at 84
+constexpr int kStateWords = 15;
+
+// Everything a launch needs, passed by value (__grid_constant__).
+struct Params {
+    // engine configuration (StConfig, pre-digested on the host)
+    int W, H;
+    int lock_mod;  // max(lock_delay,0)+1, ref:175
+    int step_reset, auto_reset;
+    int reward_step, pen_height, pen_height_inc, adv_clears, high_scoring, pen_holes, pen_holes_inc;
+    uint32_t fullmask;
+    int row_bytes;  // 2 (W<=16) or 4
+    int stride;     // bytes per env record
+    uint32_t seed_lo, seed_hi;
+    long long env_id_base;
+    // observation geometry (closed form of ref:76-114 at size 84)
+    int obs_elems;
+    int pitch, gap, inner_v, inner_h, pad_top, pad_left;
+    uint32_t inv_h20;   // ceil(2^20 / H)      : i / H      for i < 2048
+    uint32_t inv_hq20;  // ceil(2^20 / (H/4))  : q / (H/4)  when H % 4 == 0
+    // buffers
+    unsigned char *state;
+    const uint8_t *actions;
+    float *obs;
+    float *reward;
+    uint8_t *done;
+    int32_t *info;
+    const uint8_t *mask;
+    const uint8_t *queue;
+    int queue_len;
+    int *err;
+    unsigned long long *stats;
+    long long n;
+    int T;
+    long long obs_t_stride, info_t_stride;
+    int mode;
+    int draw_piece;
+};
+
+cudaError_t launch_main(const Params &p, int obs_type, cudaStream_t stream);
+cudaError_t launch_init(const Params &p, cudaStream_t stream);
+cudaError_t launch_get_state(const Params &p, uint8_t *boards, int32_t *scalars, cudaStream_t stream);
+cudaError_t launch_set_state(const Params &p, const uint8_t *boards, const int32_t *scalars, cudaStream_t stream);
+unsigned long long launch_count();
+
+}  // namespace st

@@ -1,0 +1,721 @@
+// SimpleTetris step path for sm_100a: one warp per env, one board row per lane.
+//
+// What the reference does in tetris_env.py:10-335 + 397-433 (cited as ref:LINE) on a dense float64
+// (W,H) array is done here on a row bitboard held in registers: lane l of the env's warp owns row l
+// (and row l+32 when H > 31).  Collision for EVERY anchor height at once is an AND of shifted piece
+// row masks followed by one warp OR-reduction (REDUX), so soft drop, hard drop, gravity and the
+// grounded test all read the same mask.  Line clear is compare-to-full + ballot + shuffle compaction,
+// holes are a shuffle prefix-OR + popc, height is popc of a ballot.  Control flow is uniform per warp
+// (one env), so the rare lock / spawn / reset branches cost nothing when they are not taken.
+// Observations: ram is expanded by the env's own warp from a 128-byte smem staging row with 16-byte
+// stores; 84x84 images are written by the whole CTA (8 envs) with every thread owning a fixed
+// 16-byte column slot, so a warp store covers 512 contiguous bytes.
+#include "st_internal.h"
+
+namespace st {
+
+// ---------------------------------------------------------------------------------------------
+// Piece table: 7 pieces x 4 rotations.  Entry = 7x7 bit grid, bit (j+3)*7 + (i+3) for cell offset
+// (i,j) from the anchor (ref:10-19), rotation r = r applications of (i,j)->(j,-i) (ref:22-26).
+// ---------------------------------------------------------------------------------------------
+struct PieceTab {
+    unsigned long long m[28];
+    signed char minj[28];
+    signed char maxj[28];
+};
+
+constexpr PieceTab make_piece_tab()
+{
+    const int base[7][4][2] = {
+        {{0, 0}, {-1, 0}, {1, 0}, {0, -1}},    // T
+        {{0, 0}, {-1, 0}, {0, -1}, {0, -2}},   // J
+        {{0, 0}, {1, 0}, {0, -1}, {0, -2}},    // L
+        {{0, 0}, {-1, 0}, {0, -1}, {1, -1}},   // Z
+        {{0, 0}, {-1, -1}, {0, -1}, {1, 0}},   // S
+        {{0, 0}, {0, -1}, {0, -2}, {0, -3}},   // I
+        {{0, 0}, {0, -1}, {-1, 0}, {-1, -1}},  // O
+    };
+    PieceTab t{};
+    for (int id = 0; id < 7; ++id) {
+        int c[4][2] = {};
+        for (int k = 0; k < 4; ++k) { c[k][0] = base[id][k][0]; c[k][1] = base[id][k][1]; }
+        for (int r = 0; r < 4; ++r) {
+            unsigned long long m = 0;
+            int mn = 0, mx = 0;
+            for (int k = 0; k < 4; ++k) {
+                int i = c[k][0], j = c[k][1];
+                m |= 1ull << ((j + 3) * 7 + (i + 3));
+                mn = j < mn ? j : mn;
+                mx = j > mx ? j : mx;
+            }
+            t.m[id * 4 + r] = m;
+            t.minj[id * 4 + r] = (signed char)mn;
+            t.maxj[id * 4 + r] = (signed char)mx;
+            for (int k = 0; k < 4; ++k) { int i = c[k][0], j = c[k][1]; c[k][0] = j; c[k][1] = -i; }
+        }
+    }
+    return t;
+}
+
+__constant__ PieceTab c_tab = make_piece_tab();
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// ---------------------------------------------------------------------------------------------
+// Piece rows at column x.  Row t is piece row j = minj + t (rows past maxj are empty).
+//   mb[t]   in-board cells of that row as a board-row mask
+//   wall    bit t: that row has a cell at X < 0 or X >= W   (ref:34 wall test)
+// ---------------------------------------------------------------------------------------------
+struct PieceRows {
+    uint32_t mb[4];
+    uint32_t wall;
+    int minj, maxj;
+};
+
+__device__ __forceinline__ PieceRows piece_rows(int id, int rot, int x, int W, uint32_t fullmask)
+{
+    const int s = id * 4 + rot;
+    const unsigned long long m = c_tab.m[s];
+    PieceRows pr;
+    pr.minj = c_tab.minj[s];
+    pr.maxj = c_tab.maxj[s];
+    pr.wall = 0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int j = pr.minj + t;  // <= 3 because minj <= 0
+        const uint32_t m7 = (uint32_t)(m >> ((j + 3) * 7)) & 127u;
+        const uint32_t mb = x >= 3 ? (m7 << (x - 3)) : (m7 >> (3 - x));
+        const int lo = x - 3 + (__ffs((int)m7) - 1);
+        const int hi = x - 3 + (31 - __clz((int)m7));
+        const uint32_t wall = (m7 != 0u) && (lo < 0 || hi >= W);
+        pr.mb[t] = mb & fullmask;
+        pr.wall |= wall << t;
+    }
+    return pr;
+}
+
+template <int RPL> struct CMask { using type = uint32_t; };
+template <> struct CMask<2> { using type = unsigned long long; };
+
+__device__ __forceinline__ uint32_t warp_or(uint32_t v) { return __reduce_or_sync(FULL, v); }
+__device__ __forceinline__ unsigned long long warp_or(unsigned long long v)
+{
+    uint32_t lo = __reduce_or_sync(FULL, (uint32_t)v);
+    uint32_t hi = __reduce_or_sync(FULL, (uint32_t)(v >> 32));
+    return ((unsigned long long)hi << 32) | lo;
+}
+__device__ __forceinline__ int ctz(uint32_t v) { return __ffs((int)v) - 1; }
+__device__ __forceinline__ int ctz(unsigned long long v) { return __ffsll((long long)v) - 1; }
+
+// Collision mask over anchor heights: bit y' set <=> is_occupied(shape, (x, y'), board) (ref:29-36).
+// Rows with Y < 0 have no lane, so they are skipped for board AND walls, exactly like ref:32-33.
+template <int RPL>
+__device__ __forceinline__ typename CMask<RPL>::type collision_mask(const uint32_t (&row)[RPL], const PieceRows &pr,
+                                                                    int H, int lane)
+{
+    using M = typename CMask<RPL>::type;
+    constexpr int BITS = 32 * RPL;
+    M c = 0;
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) {
+        const int Y = lane + 32 * k;
+        if (Y < H) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int yp = Y - (pr.minj + t);
+                const bool hit = ((pr.wall >> t) & 1u) || ((pr.mb[t] & row[k]) != 0u);
+                if (hit && yp >= 0 && yp < BITS) c |= (M)1 << yp;
+            }
+        }
+    }
+    c = warp_or(c);
+    int fl = H - pr.maxj;  // anchors whose lowest cell is at or below the floor (ref:34 `y >= board.shape[1]`)
+    fl = fl < 0 ? 0 : fl;
+    c |= ~(M)0 << fl;
+    return c;
+}
+
+// Philox4x32-10 keyed by the run seed, counter = (global env id, lifetime piece index).
+__device__ __forceinline__ uint32_t philox_draw(uint32_t k0, uint32_t k1, unsigned long long env_id, uint32_t index)
+{
+    uint32_t c0 = (uint32_t)env_id, c1 = (uint32_t)(env_id >> 32), c2 = index, c3 = 0;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return c0;
+}
+
+// _new_piece / _choose_shape (ref:183-200).  `sw` is this lane's word of the env record (lanes 8..14
+// hold shape_counts).  Returns the piece id; bumps its count.
+__device__ __forceinline__ int spawn_piece(int &sw, int lane, const Params &p, long long e, int &errbits)
+{
+    int c[7];
+    int total = 0, mx = 0;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        c[i] = __shfl_sync(FULL, sw, 8 + i);
+        total += c[i];
+        mx = c[i] > mx ? c[i] : mx;
+    }
+    int id;
+    if (p.queue) {
+        int k = total;
+        if (k >= p.queue_len) { errbits |= 1; k %= p.queue_len; }
+        id = p.queue[e * p.queue_len + k] % 7;
+    } else {
+        const int S = 35 + 7 * mx - total;  // sum of m_i = 5 + max - c_i (ref:186)
+        const uint32_t u = philox_draw(p.seed_lo, p.seed_hi, (unsigned long long)(p.env_id_base + e), (uint32_t)total);
+        const int r = 1 + (int)__umulhi(u, (uint32_t)S);  // uniform on [1, S] (ref:187)
+        int acc = 0;
+        id = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {  // smallest i with cumsum(m)[i] >= r (ref:188-191)
+            acc += 5 + mx - c[i];
+            id += (r > acc) ? 1 : 0;
+        }
+    }
+    if (lane == 8 + id) sw += 1;
+    return id;
+}
+
+// Rows [0, fr] shift down by one (row 0 becomes empty): removal of full row `fr` (ref:205-216).
+template <int RPL>
+__device__ __forceinline__ void remove_row(uint32_t (&row)[RPL], int fr, int lane)
+{
+    if (RPL == 1) {
+        const uint32_t up = __shfl_up_sync(FULL, row[0], 1);
+        if (lane <= fr) row[0] = lane ? up : 0u;
+    } else {
+        const uint32_t up0 = __shfl_up_sync(FULL, row[0], 1);
+        const uint32_t up1 = __shfl_up_sync(FULL, row[RPL - 1], 1);
+        const uint32_t last0 = __shfl_sync(FULL, row[0], 31);
+        if (lane + 32 <= fr) row[RPL - 1] = lane ? up1 : last0;
+        if (lane <= fr) row[0] = lane ? up0 : 0u;
+    }
+}
+
+// _count_holes (ref:218-220): empty cells with a filled cell above them in the same column.
+template <int RPL>
+__device__ __forceinline__ int count_holes(const uint32_t (&row)[RPL], int H, uint32_t fullmask, int lane)
+{
+    int cnt = 0;
+    uint32_t carry = 0;  // OR of all rows of the previous 32-row block
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) {
+        uint32_t v = row[k];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, v, d);
+            if (lane >= d) v |= t;
+        }
+        uint32_t above = __shfl_up_sync(FULL, v, 1);
+        if (lane == 0) above = 0;
+        above |= carry;
+        if (lane + 32 * k < H) cnt += __popc(above & ~row[k] & fullmask);
+        if (k + 1 < RPL) carry |= __shfl_sync(FULL, v, 31);
+    }
+    return __reduce_add_sync(FULL, cnt);
+}
+
+template <int RPL>
+__device__ __forceinline__ int nonempty_rows(const uint32_t (&row)[RPL])
+{
+    int n = 0;
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) n += __popc(__ballot_sync(FULL, row[k] != 0u));
+    return n;
+}
+
+// The piece's cells on this lane's rows (ref:323-327 _set_piece: in-bounds cells only).
+template <int RPL>
+__device__ __forceinline__ void piece_on_rows(uint32_t (&pm)[RPL], const PieceRows &pr, int y, int lane)
+{
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) {
+        const int t = lane + 32 * k - y - pr.minj;
+        uint32_t m = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) m = (t == q) ? pr.mb[q] : m;
+        pm[k] = m;
+    }
+}
+
+// Warp-uniform engine state (the scalars live in `sw`, one word per lane, between uses).
+struct Piece {
+    int id, rot, x, y;
+};
+__device__ __forceinline__ int pack_piece(const Piece &pc) { return pc.id | (pc.rot << 4) | (pc.x << 8) | (pc.y << 16); }
+__device__ __forceinline__ Piece unpack_piece(int w)
+{
+    Piece pc;
+    pc.id = w & 15; pc.rot = (w >> 4) & 3; pc.x = (w >> 8) & 255; pc.y = (w >> 16) & 255;
+    return pc;
+}
+
+__device__ __forceinline__ void put(int &sw, int lane, int idx, int v) { if (lane == idx) sw = v; }
+__device__ __forceinline__ int get(int sw, int idx) { return __shfl_sync(FULL, sw, idx); }
+
+// clear() (ref:306-315): zero the per-episode counters, spawn, empty board.  The lock-delay counter,
+// deaths and shape_counts persist.
+template <int RPL>
+__device__ __forceinline__ void engine_clear(uint32_t (&row)[RPL], int &sw, Piece &pc, int lane, const Params &p,
+                                             long long e, int &errbits)
+{
+    if (lane >= 2 && lane <= 6) sw = 0;  // time, score, lines_cleared, holes, piece_height
+    pc.id = spawn_piece(sw, lane, p, e, errbits);
+    pc.rot = 0; pc.x = p.W / 2; pc.y = 0;
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) row[k] = 0;
+}
+
+// TetrisEngine.step (ref:243-304).  Outputs reward/done and the display rows (board | piece, ref:301-302).
+template <int RPL>
+__device__ __forceinline__ void engine_step(uint32_t (&row)[RPL], uint32_t (&disp)[RPL], int &sw, Piece &pc, int action,
+                                            int lane, const Params &p, long long e, int &reward, int &done,
+                                            int &errbits)
+{
+    using M = typename CMask<RPL>::type;
+    const int H = p.H, W = p.W;
+    reward = p.reward_step ? 1 : 0;  // ref:256
+    done = 0;
+    if (pc.id >= 7) {  // no piece yet: the reference would fail on shape None (ref:170-172,245)
+        errbits |= 4;
+#pragma unroll
+        for (int k = 0; k < RPL; ++k) disp[k] = row[k];
+        return;
+    }
+    if (action > 6) { errbits |= 2; action = 6; }
+
+    // ---- action (ref:245, 39-73): try the move, keep it unless it collides ----
+    int r2 = pc.rot, x2 = pc.x;
+    if (action == 0) x2 -= 1;
+    if (action == 1) x2 += 1;
+    if (action == 4) r2 = (r2 + 1) & 3;
+    if (action == 5) r2 = (r2 + 3) & 3;
+    PieceRows pr = piece_rows(pc.id, r2, x2, W, p.fullmask);
+    M cm = collision_mask<RPL>(row, pr, H, lane);
+    const bool moved = (r2 != pc.rot) || (x2 != pc.x);
+    if (moved && ((cm >> pc.y) & 1)) {  // blocked: stay (ref:41,46,64,69)
+        pr = piece_rows(pc.id, pc.rot, pc.x, W, p.fullmask);
+        cm = collision_mask<RPL>(row, pr, H, lane);
+    } else {
+        pc.rot = r2; pc.x = x2;
+    }
+    int y = pc.y;
+    if (action == 3 && !((cm >> (y + 1)) & 1)) y += 1;  // soft_drop (ref:49-51)
+    if (action == 2) {                                   // hard_drop (ref:54-59): first blocked height below
+        const M above = cm >> (y + 1);
+        if (above) y += ctz(above);
+    }
+    // ---- gravity (ref:247-250) ----
+    int ld = get(sw, 1);
+    if (!((cm >> (y + 1)) & 1)) {
+        y += 1;
+        if (p.step_reset) ld = 0;
+    }
+    pc.y = y;
+    if (lane == 2) sw += 1;  // time += 1 (ref:253)
+
+    // ---- grounded -> lock delay -> lock (ref:259-299) ----
+    if ((cm >> (y + 1)) & 1) {
+        ld = (ld + 1) % p.lock_mod;  // ref:175,260
+        if (ld == 0) {
+            uint32_t pm[RPL];
+            piece_on_rows<RPL>(pm, pr, y, lane);
+#pragma unroll
+            for (int k = 0; k < RPL; ++k) row[k] |= pm[k];  // _set_piece(True) ref:263
+            // _clear_lines (ref:205-216)
+            unsigned long long full = 0;
+#pragma unroll
+            for (int k = 0; k < RPL; ++k)
+                full |= (unsigned long long)__ballot_sync(FULL, (lane + 32 * k < H) && row[k] == p.fullmask) << (32 * k);
+            const int k_cleared = __popcll(full);
+            if (k_cleared) {
+                unsigned long long f = full;
+                while (f) {  // top-most full row first; rows below it keep their index
+                    const int fr = __ffsll((long long)f) - 1;
+                    f &= f - 1;
+                    remove_row<RPL>(row, fr, lane);
+                }
+                if (lane == 4) sw += k_cleared;  // lines_cleared (ref:213)
+            }
+            // line-clear reward / score (ref:266-275)
+            int dscore;
+            if (p.adv_clears) {
+                const int kk = k_cleared > 4 ? 4 : k_cleared;
+                dscore = kk == 0 ? 0 : kk == 1 ? 40 : kk == 2 ? 100 : kk == 3 ? 300 : 1200;
+                reward += (dscore * 5) / 2;  // 2.5 * {0,40,100,300,1200} is integral
+            } else if (p.high_scoring) {
+                dscore = k_cleared;
+                reward += 1000 * k_cleared;
+            } else {
+                dscore = k_cleared;
+                reward += 100 * k_cleared;
+            }
+            if (lane == 3) sw += dscore;
+            const int old_holes = get(sw, 5);
+            const int holes = count_holes<RPL>(row, H, p.fullmask, lane);  // ref:278,284
+            put(sw, lane, 5, holes);
+            const bool top = (__ballot_sync(FULL, row[0] != 0u) & 1u) != 0u;  // np.any(board[:,0]) ref:277
+            if (top) {
+                if (lane == 7) sw += 1;  // n_deaths (ref:279)
+                done = 1;
+                reward = -100;  // ref:281 overrides everything
+            } else {
+                if (p.pen_height) {  // ref:286-287
+                    reward -= nonempty_rows<RPL>(row);
+                } else if (p.pen_height_inc) {  // ref:288-292
+                    const int nh = nonempty_rows<RPL>(row);
+                    const int ph = get(sw, 6);
+                    if (nh > ph) reward -= 10 * (nh - ph);
+                    put(sw, lane, 6, nh);
+                }
+                if (p.pen_holes) reward -= 5 * holes;  // ref:294-297
+                else if (p.pen_holes_inc) reward -= 5 * (holes - old_holes);
+                pc.id = spawn_piece(sw, lane, p, e, errbits);  // _new_piece ref:299
+                pc.rot = 0; pc.x = W / 2; pc.y = 0;
+                pr = piece_rows(pc.id, 0, pc.x, W, p.fullmask);
+            }
+        }
+    }
+    put(sw, lane, 1, ld);
+    // ---- compose the returned state (ref:301-303): draw, copy, erase ----
+    uint32_t pm[RPL];
+    piece_on_rows<RPL>(pm, pr, pc.y, lane);
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) {
+        disp[k] = row[k] | pm[k];
+        row[k] &= ~pm[k];  // _set_piece(False) also wipes a just-locked piece after game over (ref:303)
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Observation writers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float bitf(uint32_t r, int x) { return ((r >> x) & 1u) ? 1.0f : 0.0f; }
+
+// ram (ref:421-424 + float32 cast ref:400): out[x][y] = cell (x,y); rows come from the warp's smem row.
+__device__ __forceinline__ void write_ram(const uint32_t *srow, float *out, const Params &p, int lane)
+{
+    const int H = p.H, W = p.W;
+    if ((H & 3) == 0) {
+        const int nq = (W * H) >> 2;
+        float4 *o4 = reinterpret_cast<float4 *>(out);
+        for (int q = lane; q < nq; q += 32) {
+            const int x = (int)(((uint32_t)q * p.inv_hq20) >> 20);
+            const int y0 = (q - x * (H >> 2)) << 2;
+            const uint4 r = *reinterpret_cast<const uint4 *>(srow + y0);
+            o4[q] = make_float4(bitf(r.x, x), bitf(r.y, x), bitf(r.z, x), bitf(r.w, x));
+        }
+    } else {
+        const int nel = W * H;
+        for (int i = lane; i < nel; i += 32) {
+            const int x = (int)(((uint32_t)i * p.inv_h20) >> 20);
+            const int yy = i - x * H;
+            out[i] = bitf(srow[yy], x);
+        }
+    }
+}
+
+// Per-thread constants of the image writers: this thread always writes float4 slot `k` of an image row.
+struct ColSlot {
+    float lo[4], hi[4];
+    uint32_t mk[4];
+};
+
+template <int CH>
+__device__ __forceinline__ ColSlot make_col_slot(int k, const Params &p)
+{
+    ColSlot cs;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = (4 * k + i) / CH;  // pixel column
+        const int cc = c - p.pad_left;
+        const bool inside = cc >= 0 && cc < p.inner_h;
+        const bool cell = inside && (cc % p.pitch) >= p.gap;
+        cs.lo[i] = inside ? 128.0f : 0.0f;            // background / border shade (ref:77-78)
+        cs.hi[i] = cell ? 190.0f : cs.lo[i];           // piece shade (ref:79)
+        cs.mk[i] = cell ? (1u << (cc / p.pitch)) : 0u;
+    }
+    return cs;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The step / reset / observe kernel.  OBS: 0 ram, 1 grayscale, 2 rgb.
+// ---------------------------------------------------------------------------------------------
+template <int RPL, int OBS>
+__global__ void __launch_bounds__(kThreads) st_main_kernel(const __grid_constant__ Params p)
+{
+    __shared__ __align__(16) uint32_t s_disp[kWarpsPerCta][64];
+    __shared__ signed char s_rowy[kImage];
+    __shared__ unsigned char s_active[kWarpsPerCta];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int H = p.H;
+    constexpr int CH = OBS == 2 ? 3 : 1;
+    constexpr int KPR = kImage * CH / 4;  // float4 slots per image row: 21 / 63
+    constexpr int NG = 252 / KPR;         // row groups: 12 / 4
+    ColSlot cs;
+    int slot_k = 0, slot_g = 0;
+    if (OBS != 0) {
+        slot_k = threadIdx.x % KPR;
+        slot_g = threadIdx.x / KPR;
+        cs = make_col_slot<CH>(slot_k, p);
+        if (threadIdx.x < kImage) {  // image row -> board row (-1 gap row, -2 border row)
+            const int rr = (int)threadIdx.x - p.pad_top;
+            s_rowy[threadIdx.x] = (rr < 0 || rr >= p.inner_v) ? -2 : ((rr % p.pitch) < p.gap ? -1 : rr / p.pitch);
+        }
+    }
+
+    const long long ngroups = (p.n + kWarpsPerCta - 1) / kWarpsPerCta;
+    for (long long g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        const long long e = g * kWarpsPerCta + warp;
+        const bool valid = e < p.n;
+        uint32_t row[RPL], disp[RPL];
+        int sw = 0, errbits = 0;
+        Piece pc = {7, 0, 0, 0};
+        unsigned char *rec = p.state + (valid ? e : 0) * (long long)p.stride;
+        bool selected = valid;
+        if (valid) {
+            if (p.mode == MODE_RESET && p.mask && p.mask[e] == 0) selected = false;
+        }
+        if (selected) {
+            if (lane < kStateWords) sw = reinterpret_cast<const int *>(rec)[lane];
+#pragma unroll
+            for (int k = 0; k < RPL; ++k) {
+                const int Y = lane + 32 * k;
+                uint32_t v = 0;
+                if (Y < H) v = p.row_bytes == 2 ? (uint32_t)reinterpret_cast<const uint16_t *>(rec + 4 * kStateWords)[Y]
+                                                : reinterpret_cast<const uint32_t *>(rec + 4 * kStateWords)[Y];
+                row[k] = v;
+            }
+            pc = unpack_piece(get(sw, 0));
+        } else {
+#pragma unroll
+            for (int k = 0; k < RPL; ++k) row[k] = 0;
+        }
+        uint32_t row_in[RPL];
+#pragma unroll
+        for (int k = 0; k < RPL; ++k) row_in[k] = row[k];
+
+        const int T = p.mode == MODE_STEP ? p.T : 1;
+        for (int t = 0; t < T; ++t) {
+            if (selected) {
+                int reward = 0, done = 0;
+                if (p.mode == MODE_STEP) {
+                    const int action = p.actions[(long long)t * p.n + e];
+                    engine_step<RPL>(row, disp, sw, pc, action, lane, p, e, reward, done, errbits);
+                    put(sw, lane, 0, pack_piece(pc));
+                    if (p.info && lane < kStateWords)  // get_info (ref:232-241) before any auto-reset
+                        p.info[(long long)t * p.info_t_stride + e * kStateWords + lane] = lane == 0 ? pc.id : sw;
+                    if (done) {
+                        if (p.stats && lane >= 2 && lane <= 4)  // sum(time), sum(score), sum(lines) at done
+                            atomicAdd(p.stats + (lane == 2 ? 1 : lane == 3 ? 3 : 2), (unsigned long long)(long long)sw);
+                        if (p.stats && lane == 0) atomicAdd(p.stats, 1ull);
+                        if (p.auto_reset) {  // VecEnv: reset obs = empty board, piece not drawn (ref:313-315)
+                            engine_clear<RPL>(row, sw, pc, lane, p, e, errbits);
+                            put(sw, lane, 0, pack_piece(pc));
+#pragma unroll
+                            for (int k = 0; k < RPL; ++k) disp[k] = 0;
+                        }
+                    }
+                    if (lane == 0) {
+                        p.reward[(long long)t * p.n + e] = (float)reward;
+                        p.done[(long long)t * p.n + e] = (unsigned char)done;
+                    }
+                } else if (p.mode == MODE_RESET) {
+                    engine_clear<RPL>(row, sw, pc, lane, p, e, errbits);
+                    put(sw, lane, 0, pack_piece(pc));
+#pragma unroll
+                    for (int k = 0; k < RPL; ++k) disp[k] = 0;
+                } else {  // MODE_OBSERVE: engine.render() (ref:317-321) or the bare board
+                    uint32_t pm[RPL];
+#pragma unroll
+                    for (int k = 0; k < RPL; ++k) pm[k] = 0;
+                    if (p.draw_piece && pc.id < 7) {
+                        const PieceRows pr = piece_rows(pc.id, pc.rot, pc.x, p.W, p.fullmask);
+                        piece_on_rows<RPL>(pm, pr, pc.y, lane);
+                    }
+#pragma unroll
+                    for (int k = 0; k < RPL; ++k) disp[k] = row[k] | pm[k];
+                }
+                if (p.obs) {
+#pragma unroll
+                    for (int k = 0; k < RPL; ++k) s_disp[warp][lane + 32 * k] = disp[k];
+                }
+            }
+            float *obs_t = p.obs ? p.obs + (long long)t * p.obs_t_stride : nullptr;
+            if (OBS == 0) {
+                __syncwarp();
+                if (selected && obs_t) write_ram(s_disp[warp], obs_t + e * (long long)p.obs_elems, p, lane);
+                __syncwarp();
+            } else {
+                if (lane == 0) s_active[warp] = selected && obs_t;
+                __syncthreads();
+                if (threadIdx.x < KPR * NG) {
+                    float4 *base = reinterpret_cast<float4 *>(obs_t + g * kWarpsPerCta * (long long)p.obs_elems) + slot_k;
+                    for (int rho = slot_g; rho < kImage; rho += NG) {
+                        const int code = s_rowy[rho];
+#pragma unroll
+                        for (int w = 0; w < kWarpsPerCta; ++w) {
+                            if (!s_active[w]) continue;
+                            const uint32_t b = code >= 0 ? s_disp[w][code] : 0u;
+                            float4 v;
+                            v.x = (b & cs.mk[0]) ? cs.hi[0] : cs.lo[0];
+                            v.y = (b & cs.mk[1]) ? cs.hi[1] : cs.lo[1];
+                            v.z = (b & cs.mk[2]) ? cs.hi[2] : cs.lo[2];
+                            v.w = (b & cs.mk[3]) ? cs.hi[3] : cs.lo[3];
+                            if (code == -2) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                            base[(long long)w * (p.obs_elems >> 2) + rho * KPR] = v;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+
+        if (selected && p.mode != MODE_OBSERVE) {
+            if (lane < kStateWords) reinterpret_cast<int *>(rec)[lane] = sw;
+            bool dirty = false;
+#pragma unroll
+            for (int k = 0; k < RPL; ++k) dirty |= row[k] != row_in[k];
+            if (__any_sync(FULL, dirty)) {
+#pragma unroll
+                for (int k = 0; k < RPL; ++k) {
+                    const int Y = lane + 32 * k;
+                    if (Y < H) {
+                        if (p.row_bytes == 2) reinterpret_cast<uint16_t *>(rec + 4 * kStateWords)[Y] = (uint16_t)row[k];
+                        else reinterpret_cast<uint32_t *>(rec + 4 * kStateWords)[Y] = row[k];
+                    }
+                }
+            }
+        }
+        if (errbits && p.err && lane == 0) atomicOr(p.err, errbits);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// init / get_state / set_state: one thread per env, cold path.
+// ---------------------------------------------------------------------------------------------
+__global__ void st_init_kernel(const __grid_constant__ Params p)
+{
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= p.n) return;
+    int *w = reinterpret_cast<int *>(p.state + e * (long long)p.stride);
+    for (int i = 0; i < p.stride / 4; ++i) w[i] = 0;
+    w[0] = 7;    // no piece (ref:170-172)
+    w[2] = -1;   // time  (ref:165)
+    w[3] = -1;   // score (ref:166)
+}
+
+__global__ void st_get_state_kernel(const __grid_constant__ Params p, uint8_t *boards, int32_t *scalars)
+{
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= p.n) return;
+    const unsigned char *rec = p.state + e * (long long)p.stride;
+    const int *w = reinterpret_cast<const int *>(rec);
+    if (scalars) {
+        int32_t *s = scalars + e * 18;
+        const Piece pc = unpack_piece(w[0]);
+        s[0] = pc.id; s[1] = pc.rot; s[2] = pc.x; s[3] = pc.y;
+        for (int i = 1; i < kStateWords; ++i) s[3 + i] = w[i];
+    }
+    if (boards) {
+        for (int y = 0; y < p.H; ++y) {
+            const uint32_t r = p.row_bytes == 2 ? (uint32_t)reinterpret_cast<const uint16_t *>(rec + 60)[y]
+                                                : reinterpret_cast<const uint32_t *>(rec + 60)[y];
+            for (int x = 0; x < p.W; ++x) boards[(e * p.W + x) * p.H + y] = (r >> x) & 1u;
+        }
+    }
+}
+
+__global__ void st_set_state_kernel(const __grid_constant__ Params p, const uint8_t *boards, const int32_t *scalars)
+{
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= p.n) return;
+    unsigned char *rec = p.state + e * (long long)p.stride;
+    int *w = reinterpret_cast<int *>(rec);
+    if (scalars) {
+        const int32_t *s = scalars + e * 18;
+        Piece pc;
+        pc.id = s[0] < 0 || s[0] > 7 ? 7 : s[0];
+        pc.rot = s[1] & 3;
+        pc.x = min(max(s[2], 0), p.W - 1);
+        pc.y = min(max(s[3], 0), p.H - 1);
+        w[0] = pack_piece(pc);
+        for (int i = 1; i < kStateWords; ++i) w[i] = s[3 + i];
+    }
+    if (boards) {
+        for (int y = 0; y < p.H; ++y) {
+            uint32_t r = 0;
+            for (int x = 0; x < p.W; ++x) r |= (boards[(e * p.W + x) * p.H + y] ? 1u : 0u) << x;
+            if (p.row_bytes == 2) reinterpret_cast<uint16_t *>(rec + 60)[y] = (uint16_t)r;
+            else reinterpret_cast<uint32_t *>(rec + 60)[y] = r;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+static unsigned long long g_launches = 0;
+unsigned long long launch_count() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+static inline void count_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
+
+template <int RPL, int OBS>
+static cudaError_t launch_t(const Params &p, cudaStream_t stream)
+{
+    const long long ngroups = (p.n + kWarpsPerCta - 1) / kWarpsPerCta;
+    if (ngroups == 0) return cudaSuccess;
+    const long long maxgrid = 1ll << 30;
+    const unsigned grid = (unsigned)(ngroups < maxgrid ? ngroups : maxgrid);
+    st_main_kernel<RPL, OBS><<<grid, kThreads, 0, stream>>>(p);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_main(const Params &p, int obs_type, cudaStream_t stream)
+{
+    const int rpl = p.H > 31 ? 2 : 1;
+    switch (rpl * 10 + obs_type) {
+    case 10: return launch_t<1, 0>(p, stream);
+    case 11: return launch_t<1, 1>(p, stream);
+    case 12: return launch_t<1, 2>(p, stream);
+    case 20: return launch_t<2, 0>(p, stream);
+    case 21: return launch_t<2, 1>(p, stream);
+    case 22: return launch_t<2, 2>(p, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+static inline unsigned cold_grid(long long n) { return (unsigned)((n + 127) / 128); }
+
+cudaError_t launch_init(const Params &p, cudaStream_t stream)
+{
+    if (p.n == 0) return cudaSuccess;
+    st_init_kernel<<<cold_grid(p.n), 128, 0, stream>>>(p);
+    count_launch();
+    return cudaGetLastError();
+}
+cudaError_t launch_get_state(const Params &p, uint8_t *boards, int32_t *scalars, cudaStream_t stream)
+{
+    if (p.n == 0) return cudaSuccess;
+    st_get_state_kernel<<<cold_grid(p.n), 128, 0, stream>>>(p, boards, scalars);
+    count_launch();
+    return cudaGetLastError();
+}
+cudaError_t launch_set_state(const Params &p, const uint8_t *boards, const int32_t *scalars, cudaStream_t stream)
+{
+    if (p.n == 0) return cudaSuccess;
+    st_set_state_kernel<<<cold_grid(p.n), 128, 0, stream>>>(p, boards, scalars);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace st

@@ -1,0 +1,199 @@
+"""`TetrisEnv`: the reference's single-env class (tetris_env.py:338-467) as an N=1 view of the CUDA path.
+
+Same constructor kwargs, spaces, `step`/`reset` tuple shapes, reward values and info keys as the
+reference; NumPy in, NumPy out.  It owns a `st_host_*` handle (include/simpletetris_b200.h), so it needs
+neither torch nor a caller-side device allocator.  `env.engine` is a read/write view of the device
+state with the attribute names of the reference's `TetrisEngine` (tetris_env.py:125-181).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import random
+
+import numpy as np
+
+from .. import native
+from ..spaces import Box, Discrete
+
+shape_names = ["T", "J", "L", "Z", "S", "I", "O"]  # tetris_env.py:19
+shapes = {  # tetris_env.py:10-18 (kept for callers that read `engine.shape`)
+    "T": [(0, 0), (-1, 0), (1, 0), (0, -1)], "J": [(0, 0), (-1, 0), (0, -1), (0, -2)],
+    "L": [(0, 0), (1, 0), (0, -1), (0, -2)], "Z": [(0, 0), (-1, 0), (0, -1), (1, -1)],
+    "S": [(0, 0), (-1, -1), (0, -1), (1, 0)], "I": [(0, 0), (0, -1), (0, -2), (0, -3)],
+    "O": [(0, 0), (0, -1), (-1, 0), (-1, -1)],
+}
+
+try:
+    import gym as _gym  # type: ignore
+
+    _Base = _gym.Env
+except Exception:  # noqa: BLE001
+    try:
+        import gymnasium as _gym  # type: ignore
+
+        _Base = _gym.Env
+    except Exception:  # noqa: BLE001
+        _Base = object
+
+
+class EngineView:
+    """Attribute view of the one env's device state (names of tetris_env.py:138-181)."""
+
+    def __init__(self, env):
+        self._env = env
+        self.width, self.height = env.width, env.height
+
+    def _scalars(self):
+        s = np.zeros((1, native.ST_UNPACKED_WORDS), dtype=np.int32)
+        native.check(self._env._L.st_host_get_state(self._env._h, None, s.ctypes.data), "st_host_get_state")
+        return s[0]
+
+    def _set_scalar(self, idx, value):
+        s = self._scalars().reshape(1, -1).copy()
+        s[0, idx] = value
+        native.check(self._env._L.st_host_set_state(self._env._h, None, s.ctypes.data), "st_host_set_state")
+
+    @property
+    def board(self):
+        b = np.zeros((1, self.width, self.height), dtype=np.uint8)
+        native.check(self._env._L.st_host_get_state(self._env._h, b.ctypes.data, None), "st_host_get_state")
+        return b[0].astype(np.float64)
+
+    @board.setter
+    def board(self, value):
+        b = np.ascontiguousarray(np.asarray(value) != 0, dtype=np.uint8).reshape(1, self.width, self.height)
+        native.check(self._env._L.st_host_set_state(self._env._h, b.ctypes.data, None), "st_host_set_state")
+
+    shape_name = property(lambda self: shape_names[self._scalars()[0]] if self._scalars()[0] < 7 else None)
+    anchor = property(lambda self: (int(self._scalars()[2]), int(self._scalars()[3])) if self._scalars()[0] < 7 else None)
+    _lock_delay = property(lambda self: int(self._scalars()[4]), lambda self, v: self._set_scalar(4, v))
+    time = property(lambda self: int(self._scalars()[5]), lambda self, v: self._set_scalar(5, v))
+    score = property(lambda self: int(self._scalars()[6]), lambda self, v: self._set_scalar(6, v))
+    lines_cleared = property(lambda self: int(self._scalars()[7]), lambda self, v: self._set_scalar(7, v))
+    holes = property(lambda self: int(self._scalars()[8]), lambda self, v: self._set_scalar(8, v))
+    piece_height = property(lambda self: int(self._scalars()[9]), lambda self, v: self._set_scalar(9, v))
+    n_deaths = property(lambda self: int(self._scalars()[10]), lambda self, v: self._set_scalar(10, v))
+
+    @property
+    def shape(self):
+        s = self._scalars()
+        if s[0] >= 7:
+            return None
+        cells = list(shapes[shape_names[s[0]]])
+        for _ in range(int(s[1])):  # rotated(cclk=False), tetris_env.py:22-26
+            cells = [(j, -i) for i, j in cells]
+        return cells
+
+    @property
+    def shape_counts(self):
+        s = self._scalars()
+        return {n: int(s[11 + i]) for i, n in enumerate(shape_names)}
+
+    def set_piece(self, name, rot=0, x=None, y=0):
+        """Replace the active piece (test hook; the reference's tests would assign engine.shape/anchor)."""
+        s = self._scalars().reshape(1, -1).copy()
+        s[0, 0] = shape_names.index(name) if isinstance(name, str) else int(name)
+        s[0, 1], s[0, 2], s[0, 3] = rot, self.width // 2 if x is None else x, y
+        native.check(self._env._L.st_host_set_state(self._env._h, None, s.ctypes.data), "st_host_set_state")
+
+    def set_pieces(self, pieces):
+        """Inject the lifetime piece sequence (the `_choose_shape` replacement used by parity tests)."""
+        q = np.asarray([shape_names.index(p) if isinstance(p, str) else int(p) for p in pieces], dtype=np.uint8)
+        native.check(self._env._L.st_host_set_piece_queue(self._env._h, q.ctypes.data, len(q)),
+                     "st_host_set_piece_queue")
+
+    def get_info(self):
+        return self._env._get_info()
+
+
+class TetrisEnv(_Base):
+    metadata = {"render.modes": ["human", "rgb_array"], "render_fps": 8}  # tetris_env.py:339
+
+    def __init__(self, width=10, height=20, obs_type="ram", extend_dims=False, render_mode="rgb_array",
+                 reward_step=False, penalise_height=False, penalise_height_increase=False, advanced_clears=False,
+                 high_scoring=False, penalise_holes=False, penalise_holes_increase=False, lock_delay=0,
+                 step_reset=False, *, device=0, seed=None, env_id=0):
+        self.width, self.height, self.obs_type, self.extend_dims = width, height, obs_type, extend_dims
+        self.render_mode = render_mode
+        self.window_size = 512
+        self.window = None
+        self.clock = None
+        if seed is None:  # the reference draws pieces from the global `random` (tetris_env.py:2,187);
+            seed = random.getrandbits(64)  # so `random.seed(s)` before construction fixes the piece stream
+        self._L = native.lib()
+        self._cfg = native.make_config(
+            width=width, height=height, obs_type=obs_type, extend_dims=extend_dims, lock_delay=lock_delay,
+            step_reset=step_reset, reward_step=reward_step, penalise_height=penalise_height,
+            penalise_height_increase=penalise_height_increase, advanced_clears=advanced_clears,
+            high_scoring=high_scoring, penalise_holes=penalise_holes,
+            penalise_holes_increase=penalise_holes_increase, auto_reset=False, device=device, seed=seed,
+            env_id_base=env_id)
+        self._h = self._L.st_host_create(C.byref(self._cfg), 1)
+        if not self._h:
+            raise RuntimeError("st_host_create failed: " + self._L.st_last_error().decode())
+        self.action_space = Discrete(7)  # tetris_env.py:377
+        if obs_type == "ram":  # tetris_env.py:381-392 (declared range 0..1 kept, images are 0/128/190)
+            shp = (width, height, 1) if extend_dims else (width, height)
+        elif obs_type == "grayscale":
+            shp = (84, 84, 1) if extend_dims else (84, 84)
+        else:
+            shp = (84, 84, 3)
+        if obs_type in ("ram", "grayscale", "rgb"):
+            self.observation_space = Box(0, 1, shape=shp, dtype=np.float32)
+        self._obs_shape = shp
+        self._info_buf = np.zeros((1, native.ST_INFO_WORDS), dtype=np.int32)
+        self.engine = EngineView(self)
+
+    def _get_info(self):
+        a = self._info_buf[0]
+        s = self.engine._scalars()
+        return {"time": int(s[5]), "current_piece": shape_names[s[0]] if s[0] < 7 else None, "score": int(s[6]),
+                "lines_cleared": int(s[7]), "holes": int(s[8]), "deaths": int(s[10]),
+                "statistics": {n: int(s[11 + i]) for i, n in enumerate(shape_names)}} if a is not None else {}
+
+    def step(self, action):
+        if isinstance(action, (bool, np.bool_)) or int(action) != action or not 0 <= int(action) <= 6:
+            raise KeyError(action)  # value_action_map lookup, tetris_env.py:245
+        a = np.asarray([int(action)], dtype=np.uint8)
+        obs = np.empty(self._obs_shape, dtype=np.float32)
+        reward = np.zeros(1, dtype=np.float32)
+        done = np.zeros(1, dtype=np.uint8)
+        native.check(self._L.st_host_step(self._h, a.ctypes.data, obs.ctypes.data, reward.ctypes.data,
+                                          done.ctypes.data, self._info_buf.ctypes.data), "st_host_step")
+        err = C.c_int32(0)
+        native.check(self._L.st_host_poll(self._h, C.byref(err), None), "st_host_poll")
+        if err.value & 4:
+            raise TypeError("step() called before reset(): the engine has no piece (tetris_env.py:170-172)")
+        if err.value & 1:
+            raise IndexError("injected piece queue exhausted")
+        r = float(reward[0])
+        i = self._info_buf[0]
+        info = {"time": int(i[2]), "current_piece": shape_names[i[0]], "score": int(i[3]),
+                "lines_cleared": int(i[4]), "holes": int(i[5]), "deaths": int(i[7]),
+                "statistics": {n: int(i[8 + k]) for k, n in enumerate(shape_names)}}
+        return obs, (int(r) if r.is_integer() else r), bool(done[0]), info
+
+    def reset(self, return_info=False):
+        obs = np.empty(self._obs_shape, dtype=np.float32)
+        native.check(self._L.st_host_reset(self._h, None, obs.ctypes.data), "st_host_reset")
+        return (obs, self._get_info()) if return_info else obs
+
+    def _observation(self):
+        """engine.render() through _observation (tetris_env.py:413-433): board with the piece drawn."""
+        obs = np.empty(self._obs_shape, dtype=np.float32)
+        native.check(self._L.st_host_observe(self._h, 1, obs.ctypes.data), "st_host_observe")
+        return obs
+
+    def render(self, mode="human"):
+        raise NotImplementedError("render() is display code outside the step path (SURVEY.md section 8f)")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.st_host_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass

@@ -1,0 +1,210 @@
+"""`VecEnv`: N SimpleTetris instances stepped by one CUDA launch.
+
+Same constructor kwargs as the reference `TetrisEnv` (tetris_env.py:343-357); the step/reset results
+are the batched form of tetris_env.py:397-411, with gym<=0.25 vector auto-reset: when an env is done,
+the returned observation is its reset observation and reward/done/info are the terminal step's.
+All buffers are torch tensors on the env's device; the work happens in `libsimpletetris_b200.so`
+(hand-written sm_100a kernels) through the C ABI of include/simpletetris_b200.h.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import native
+from .native import ST_INFO_WORDS, ST_STATS_WORDS, ST_UNPACKED_WORDS, StAux
+
+SHAPE_NAMES = ["T", "J", "L", "Z", "S", "I", "O"]  # piece ids 0..6, tetris_env.py:19
+# columns of the info tensor (int32 [N, 15]); get_info keys of tetris_env.py:232-241
+INFO_COLS = {"current_piece": 0, "lock_delay_counter": 1, "time": 2, "score": 3, "lines_cleared": 4, "holes": 5,
+             "piece_height": 6, "deaths": 7}
+INFO_KEYS = ("time", "current_piece", "score", "lines_cleared", "holes", "deaths", "statistics")
+
+
+def obs_shape(width, height, obs_type, extend_dims):
+    """Per-env observation shape, tetris_env.py:381-392."""
+    if obs_type == "ram":
+        return (width, height, 1) if extend_dims else (width, height)
+    if obs_type == "grayscale":
+        return (84, 84, 1) if extend_dims else (84, 84)
+    return (84, 84, 3)
+
+
+class VecEnv:
+    def __init__(self, num_envs, width=10, height=20, obs_type="ram", extend_dims=False, render_mode="rgb_array",
+                 reward_step=False, penalise_height=False, penalise_height_increase=False, advanced_clears=False,
+                 high_scoring=False, penalise_holes=False, penalise_holes_increase=False, lock_delay=0,
+                 step_reset=False, *, device="cuda", seed=0, env_id_base=0, auto_reset=True, with_info=True):
+        self._L = native.lib()
+        if not torch.cuda.is_available():
+            raise RuntimeError("gym_simpletetris_b200.VecEnv needs a CUDA device (sm_100a); there is no CPU path")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError(f"VecEnv device must be a CUDA device, got {device!r}")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.num_envs = int(num_envs)
+        self.width, self.height, self.obs_type, self.extend_dims = width, height, obs_type, extend_dims
+        self.render_mode = render_mode
+        self.seed, self.env_id_base = int(seed), int(env_id_base)
+        self.cfg = native.make_config(
+            width=width, height=height, obs_type=obs_type, extend_dims=extend_dims, lock_delay=lock_delay,
+            step_reset=step_reset, reward_step=reward_step, penalise_height=penalise_height,
+            penalise_height_increase=penalise_height_increase, advanced_clears=advanced_clears,
+            high_scoring=high_scoring, penalise_holes=penalise_holes,
+            penalise_holes_increase=penalise_holes_increase, auto_reset=auto_reset, device=self.device.index,
+            seed=seed, env_id_base=env_id_base)
+        stride = self._L.st_state_stride(C.byref(self.cfg))
+        if stride <= 0:
+            raise ValueError("unsupported geometry: width must be 1..32 and height 1..63")
+        self.state_stride = int(stride)
+        self.obs_elems = int(self._L.st_obs_elems(C.byref(self.cfg)))
+        self.single_observation_shape = obs_shape(width, height, obs_type if obs_type in native.OBS_TYPES else "rgb",
+                                                  extend_dims)
+        n, dev = self.num_envs, self.device
+        self.state = torch.zeros(n * self.state_stride, dtype=torch.uint8, device=dev)
+        self.obs = torch.zeros((n,) + self.single_observation_shape, dtype=torch.float32, device=dev)
+        self.reward = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.done = torch.zeros(n, dtype=torch.bool, device=dev)
+        self.info_buf = torch.zeros((n, ST_INFO_WORDS), dtype=torch.int32, device=dev) if with_info else None
+        self.err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.stats = torch.zeros(ST_STATS_WORDS, dtype=torch.int64, device=dev)
+        self._queue = None
+        self._aux = StAux(None, 0, 0, self.err.data_ptr(), self.stats.data_ptr())
+        self._check(self._L.st_init(C.byref(self.cfg), self.state.data_ptr(), n, self._stream()), "st_init")
+
+    # ---- plumbing ----
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @staticmethod
+    def _check(rc, what):
+        native.check(rc, what)
+
+    def _actions(self, actions, shape):
+        if not torch.is_tensor(actions):
+            actions = torch.as_tensor(np.asarray(actions))
+        if actions.dtype != torch.uint8:
+            actions = actions.to(torch.uint8)
+        actions = actions.to(self.device, non_blocking=True).contiguous()
+        if tuple(actions.shape) != shape:
+            raise ValueError(f"actions must have shape {shape}, got {tuple(actions.shape)}")
+        return actions
+
+    def _info(self, buf=None):
+        buf = self.info_buf if buf is None else buf
+        if buf is None:
+            return {}
+        d = {k: buf[..., INFO_COLS[k]] for k in INFO_KEYS if k != "statistics"}
+        d["statistics"] = buf[..., 8:15]
+        return d
+
+    # ---- the reference API, batched ----
+    def reset(self, mask=None):
+        """TetrisEnv.reset (tetris_env.py:405-411) for all envs, or those with mask[e] != 0.  Returns obs [N,...]."""
+        mptr = None
+        if mask is not None:
+            mask = torch.as_tensor(mask).to(self.device).to(torch.uint8).contiguous()
+            mptr = mask.data_ptr()
+        self._check(self._L.st_reset(C.byref(self.cfg), self.state.data_ptr(), mptr, self.obs.data_ptr(),
+                                     C.byref(self._aux), self.num_envs, self._stream()), "st_reset")
+        return self.obs
+
+    def step(self, actions):
+        """TetrisEnv.step (tetris_env.py:397-403) for N envs: (obs [N,...] f32, reward [N] f32, done [N] bool, info).
+        The returned tensors are the env's own buffers and are overwritten by the next call."""
+        a = self._actions(actions, (self.num_envs,))
+        self._check(self._L.st_step(
+            C.byref(self.cfg), self.state.data_ptr(), a.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(),
+            self.done.data_ptr(), self.info_buf.data_ptr() if self.info_buf is not None else None,
+            C.byref(self._aux), self.num_envs, self._stream()), "st_step")
+        return self.obs, self.reward, self.done, self._info()
+
+    def step_many(self, actions, rollout_obs=False, rollout_info=False):
+        """T steps in one launch.  actions [T, N].  Returns (obs, reward [T,N], done [T,N], info): obs is
+        [T,N,...] if rollout_obs else the last step's [N,...]; same for info."""
+        T = int(actions.shape[0])
+        a = self._actions(actions, (T, self.num_envs))
+        n, dev = self.num_envs, self.device
+        reward = torch.empty((T, n), dtype=torch.float32, device=dev)
+        done = torch.empty((T, n), dtype=torch.bool, device=dev)
+        obs = torch.empty((T,) + tuple(self.obs.shape), dtype=torch.float32, device=dev) if rollout_obs else self.obs
+        info = self.info_buf
+        if rollout_info and info is not None:
+            info = torch.empty((T, n, ST_INFO_WORDS), dtype=torch.int32, device=dev)
+        self._check(self._L.st_step_many(
+            C.byref(self.cfg), self.state.data_ptr(), a.data_ptr(), T, obs.data_ptr(),
+            n * self.obs_elems if rollout_obs else 0, reward.data_ptr(), done.data_ptr(),
+            info.data_ptr() if info is not None else None, n * ST_INFO_WORDS if rollout_info else 0,
+            C.byref(self._aux), n, self._stream()), "st_step_many")
+        return obs, reward, done, self._info(info)
+
+    def observe(self, draw_piece=True):
+        """_observation(engine.render()) (tetris_env.py:317-321, 413-433) of the current state, no step."""
+        out = torch.empty_like(self.obs)
+        self._check(self._L.st_observe(C.byref(self.cfg), self.state.data_ptr(), int(bool(draw_piece)),
+                                       out.data_ptr(), self.num_envs, self._stream()), "st_observe")
+        return out
+
+    def close(self):
+        self.state = self.obs = self.reward = self.done = self.info_buf = None
+
+    # ---- piece source / state injection / diagnostics ----
+    def set_piece_queue(self, queue):
+        """queue [N, Q] of piece ids 0..6 (or None): the k-th piece of env e's lifetime becomes queue[e, k]
+        instead of a draw of _choose_shape (tetris_env.py:183-191)."""
+        if queue is None:
+            self._queue = None
+            self._aux.piece_queue, self._aux.queue_len = None, 0
+            return
+        q = torch.as_tensor(np.asarray(queue)).to(torch.uint8)
+        if q.dim() == 1:
+            q = q.unsqueeze(0).expand(self.num_envs, -1)
+        if q.shape[0] != self.num_envs:
+            raise ValueError("queue must be [N, Q]")
+        self._queue = q.contiguous().to(self.device)
+        self._aux.piece_queue, self._aux.queue_len = self._queue.data_ptr(), int(self._queue.shape[1])
+
+    def get_state(self):
+        """(boards uint8 [N,W,H], scalars int32 [N,18]): id, rot, x, y, lock-delay counter, time, score,
+        lines_cleared, holes, piece_height, deaths, shape_counts[7]."""
+        boards = torch.empty((self.num_envs, self.width, self.height), dtype=torch.uint8, device=self.device)
+        scalars = torch.empty((self.num_envs, ST_UNPACKED_WORDS), dtype=torch.int32, device=self.device)
+        self._check(self._L.st_get_state(C.byref(self.cfg), self.state.data_ptr(), boards.data_ptr(),
+                                         scalars.data_ptr(), self.num_envs, self._stream()), "st_get_state")
+        return boards, scalars
+
+    def set_state(self, boards=None, scalars=None):
+        b = s = None
+        if boards is not None:
+            b = torch.as_tensor(np.asarray(boards.cpu() if torch.is_tensor(boards) else boards)).to(torch.uint8)
+            b = b.to(self.device).contiguous()
+            assert tuple(b.shape) == (self.num_envs, self.width, self.height)
+        if scalars is not None:
+            s = torch.as_tensor(np.asarray(scalars.cpu() if torch.is_tensor(scalars) else scalars)).to(torch.int32)
+            s = s.to(self.device).contiguous()
+            assert tuple(s.shape) == (self.num_envs, ST_UNPACKED_WORDS)
+        self._check(self._L.st_set_state(C.byref(self.cfg), self.state.data_ptr(),
+                                         b.data_ptr() if b is not None else None,
+                                         s.data_ptr() if s is not None else None, self.num_envs, self._stream()),
+                    "st_set_state")
+
+    def poll_errors(self) -> int:
+        """Sticky ST_ERR_* bits raised by the kernels since the last poll (synchronises)."""
+        e = int(self.err.item())
+        if e:
+            self.err.zero_()
+        return e
+
+    def episode_stats(self, reduce=True):
+        """dict(episodes, length_sum, lines_sum, score_sum) accumulated at every done; summed over all ranks
+        with one all_reduce when torch.distributed is initialised (the only collective, off the step path)."""
+        from .sharding import all_reduce_sum
+
+        s = self.stats.clone()
+        if reduce:
+            s = all_reduce_sum(s)
+        e, ln, li, sc = (int(v) for v in s.tolist())
+        return {"episodes": e, "length_sum": ln, "lines_sum": li, "score_sum": sc}

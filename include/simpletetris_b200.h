@@ -1,0 +1,166 @@
+/*
+ * simpletetris_b200.h — C ABI of the B200-native batched SimpleTetris step path.
+ *
+ * This is the drop-in boundary: everything the reference does between
+ * `TetrisEnv.step/reset` and its NumPy results (reference:
+ * gym_simpletetris/envs/tetris_env.py, cited as ref:LINE) happens behind these
+ * entry points, in hand-written sm_100a CUDA kernels.  Plain pointers and
+ * sizes only; no torch types.  All `st_*` launch functions are asynchronous on
+ * the CUDA stream passed in (`stream` is a `cudaStream_t`, 0 = legacy default
+ * stream) and never allocate or free caller memory.  Return value: 0 on
+ * success, otherwise a non-zero code (a `cudaError_t` or one of ST_E_*);
+ * `st_last_error()` gives the message for the calling thread.
+ *
+ * Ownership: the caller (the Python host keeps them in torch tensors) owns
+ * state, observation, reward, done, info, action, queue, stats and error
+ * buffers.  The `st_host_*` family is the exception: a self-contained handle
+ * that owns its device buffers and takes/returns HOST memory, for callers with
+ * no device allocator of their own (the single-env `TetrisEnv` facade, and the
+ * end-to-end benchmark).
+ */
+#ifndef SIMPLETETRIS_B200_H
+#define SIMPLETETRIS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define ST_API __attribute__((visibility("default")))
+#else
+#define ST_API
+#endif
+
+#define ST_ABI_VERSION 1
+#define ST_MAX_WIDTH 32   /* one board row = one 32-bit word (16-bit in HBM when width <= 16) */
+#define ST_MAX_HEIGHT 63  /* rows live one (height<=31) or two per lane of a warp */
+#define ST_STATE_WORDS 15 /* scalar words at the head of every env record */
+#define ST_INFO_WORDS 15  /* int32 per env in the info output */
+#define ST_UNPACKED_WORDS 18
+#define ST_STATS_WORDS 4
+
+#define ST_OBS_RAM 0       /* ref:421-424: float32 [W][H] of 0/1 */
+#define ST_OBS_GRAYSCALE 1 /* ref:426-431 + ref:76-114: float32 [84][84] of 0/128/190 */
+#define ST_OBS_RGB 2       /* ref:433 + ref:117-122: float32 [84][84][3] */
+
+#define ST_E_INVALID 1001  /* bad argument / unsupported geometry */
+#define ST_E_NODEVICE 1002
+
+/* sticky bits OR-ed by the kernels into *error_flag (device int32) */
+#define ST_ERR_QUEUE_EXHAUSTED 1 /* injected piece queue ran out (wrapped around) */
+#define ST_ERR_BAD_ACTION 2      /* action outside 0..6 (ref:245 raises KeyError) -> treated as idle */
+#define ST_ERR_NO_PIECE 4        /* step before the first reset (ref:170-172: shape is None) -> no-op */
+
+/*
+ * Replaces the constructor arguments of ref:343-357 (TetrisEnv.__init__) and
+ * ref:126-137 (TetrisEngine.__init__).  `render_mode` has no effect on the step
+ * path (ref:362 stores it, nothing reads it).  Flags are 0/1.
+ */
+typedef struct StConfig {
+    int32_t width;        /* ref:344, 1..ST_MAX_WIDTH */
+    int32_t height;       /* ref:345, 1..ST_MAX_HEIGHT */
+    int32_t obs_type;     /* ref:346, ST_OBS_* */
+    int32_t extend_dims;  /* ref:347: trailing 1 in the shape only; bytes identical */
+    int32_t lock_delay;   /* ref:356 / ref:175: counter modulo max(lock_delay,0)+1 */
+    int32_t step_reset;   /* ref:357 / ref:248-249 */
+    int32_t reward_step;              /* ref:256 */
+    int32_t penalise_height;          /* ref:286-287 */
+    int32_t penalise_height_increase; /* ref:288-292 */
+    int32_t advanced_clears;          /* ref:266-269 */
+    int32_t high_scoring;             /* ref:270-272 */
+    int32_t penalise_holes;           /* ref:294-295 */
+    int32_t penalise_holes_increase;  /* ref:296-297 */
+    int32_t auto_reset;   /* 1: VecEnv semantics (gym<=0.25): on done, clear() (ref:306-315) in the same
+                             call and return the reset observation; 0: reference single-env semantics */
+    int32_t device;       /* CUDA ordinal that owns every device pointer passed with this config */
+    int32_t reserved;
+    uint64_t seed;        /* Philox key of the piece stream (replaces the global `random`, ref:2,187) */
+    int64_t env_id_base;  /* global id of env 0 of this shard; stream of env e is keyed by base+e */
+} StConfig;
+
+/* Optional device-side extras; any pointer may be NULL. */
+typedef struct StAux {
+    const uint8_t *piece_queue; /* [n][queue_len] piece ids 0..6 (ref:19 order); replaces _choose_shape
+                                   (ref:183-191) for parity runs: the k-th piece of an env's lifetime is
+                                   queue[e][k] */
+    int32_t queue_len;
+    int32_t reserved;
+    int32_t *error_flag;        /* device int32, sticky OR of ST_ERR_* */
+    unsigned long long *stats;  /* device u64[ST_STATS_WORDS]: episodes, sum(time), sum(lines_cleared),
+                                   sum(score) accumulated at every done */
+} StAux;
+
+/* ---- sizes ------------------------------------------------------------------ */
+/* Bytes of one env record in `state`: 15 int32 scalars (packed piece, lock-delay counter, time, score,
+ * lines_cleared, holes, piece_height, deaths, shape_counts[7] — the engine attributes of ref:165-181)
+ * followed by `height` board rows, 2 bytes each when width <= 16, else 4.  100 B at 10x20. */
+ST_API int64_t st_state_stride(const StConfig *cfg);
+/* float32 elements of one env's observation (ref:381-392): W*H, 7056 or 21168. */
+ST_API int64_t st_obs_elems(const StConfig *cfg);
+
+/* ---- the step path ------------------------------------------------------------ */
+/* TetrisEngine.__init__ state (ref:140,165-181): empty board, time = score = -1, no piece. */
+ST_API int st_init(const StConfig *cfg, void *state, int64_t n, void *stream);
+
+/* TetrisEnv.reset (ref:405-411) -> TetrisEngine.clear (ref:306-315) for every env (mask == NULL) or the
+ * envs with mask[e] != 0.  Writes the reset observation (empty board, piece not drawn) of those envs
+ * into obs (may be NULL). */
+ST_API int st_reset(const StConfig *cfg, void *state, const uint8_t *mask, float *obs, const StAux *aux,
+             int64_t n, void *stream);
+
+/* TetrisEnv.step (ref:397-403) -> TetrisEngine.step (ref:243-304) + _observation (ref:413-433) for n envs.
+ *   actions [n] uint8 (ids of ref:152-160);  obs [n][st_obs_elems] float32;  reward [n] float32;
+ *   done [n] uint8;  info [n][ST_INFO_WORDS] int32 or NULL: piece id, lock-delay counter, time, score,
+ *   lines_cleared, holes, piece_height, deaths, shape_counts[7] (get_info, ref:232-241), taken after the
+ *   step and BEFORE any auto-reset. */
+ST_API int st_step(const StConfig *cfg, void *state, const uint8_t *actions, float *obs, float *reward,
+            uint8_t *done, int32_t *info, const StAux *aux, int64_t n, void *stream);
+
+/* T consecutive steps in one launch (state stays in registers between steps).  actions [T][n];
+ * reward/done [T][n]; obs and info advance by obs_t_stride / info_t_stride ELEMENTS per step (0 = every
+ * step overwrites the same [n][...] buffer, n*elems = a rollout buffer). */
+ST_API int st_step_many(const StConfig *cfg, void *state, const uint8_t *actions, int32_t T, float *obs,
+                 int64_t obs_t_stride, float *reward, uint8_t *done, int32_t *info, int64_t info_t_stride,
+                 const StAux *aux, int64_t n, void *stream);
+
+/* _observation of the current state without stepping (TetrisEngine.render, ref:317-321, when
+ * draw_piece != 0; the bare board otherwise). */
+ST_API int st_observe(const StConfig *cfg, const void *state, int32_t draw_piece, float *obs, int64_t n, void *stream);
+
+/* ---- state injection / inspection (tests, checkpoints) -------------------------- */
+/* boards [n][W][H] uint8 (ref board[x,y]);  scalars [n][ST_UNPACKED_WORDS] int32: piece id (7 = none),
+ * rotation (number of rotate_left applications, ref:22-26), anchor x, anchor y, lock-delay counter, time,
+ * score, lines_cleared, holes, piece_height, deaths, shape_counts[7].  Either pointer may be NULL. */
+ST_API int st_get_state(const StConfig *cfg, const void *state, uint8_t *boards, int32_t *scalars, int64_t n, void *stream);
+ST_API int st_set_state(const StConfig *cfg, void *state, const uint8_t *boards, const int32_t *scalars, int64_t n, void *stream);
+
+/* ---- host-buffer handle (owns its device memory; synchronous) -------------------- */
+typedef struct StHostEnv StHostEnv;
+/* Allocates state/obs/... for n envs on cfg->device and runs st_init.  NULL on failure. */
+ST_API StHostEnv *st_host_create(const StConfig *cfg, int64_t n);
+ST_API void st_host_destroy(StHostEnv *h);
+/* queue: host [n][queue_len] or NULL to go back to the Philox stream. */
+ST_API int st_host_set_piece_queue(StHostEnv *h, const uint8_t *queue, int32_t queue_len);
+/* All pointers are HOST memory (pinned memory makes the copies asynchronous until the final sync);
+ * obs/info/mask may be NULL.  Copies actions in, launches, copies results out, synchronises. */
+ST_API int st_host_reset(StHostEnv *h, const uint8_t *mask, float *obs);
+ST_API int st_host_step(StHostEnv *h, const uint8_t *actions, float *obs, float *reward, uint8_t *done, int32_t *info);
+ST_API int st_host_observe(StHostEnv *h, int32_t draw_piece, float *obs);
+ST_API int st_host_get_state(StHostEnv *h, uint8_t *boards, int32_t *scalars);
+ST_API int st_host_set_state(StHostEnv *h, const uint8_t *boards, const int32_t *scalars);
+/* Reads and clears the sticky device error flag; stats_out (u64[ST_STATS_WORDS]) may be NULL. */
+ST_API int st_host_poll(StHostEnv *h, int32_t *error_flag_out, unsigned long long *stats_out);
+
+/* ---- misc ------------------------------------------------------------------------- */
+ST_API const char *st_last_error(void);
+ST_API int st_abi_version(void);
+/* Number of kernels this library has launched in this process (all threads). */
+ST_API unsigned long long st_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMPLETETRIS_B200_H */

@@ -1,0 +1,269 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the reference-generated fixtures.
+
+Bit-exact bar: every observation byte, reward, done flag and info integer.
+"""
+import numpy as np
+import pytest
+import torch
+
+from _cases import CASES, SHAPE_NAMES
+from _golden import digest, golden
+
+pytestmark = pytest.mark.gpu
+
+ROLL = golden("rollouts.npz")
+SCEN = golden("scenarios.npz")
+INFO13 = [2, 0, 3, 4, 5, 7] + list(range(8, 15))  # my 15-word info row -> oracle/golden 13-int row
+
+
+def info_row(info):
+    return [info["time"], SHAPE_NAMES.index(info["current_piece"]), info["score"], info["lines_cleared"],
+            info["holes"], info["deaths"]] + [info["statistics"][n] for n in SHAPE_NAMES]
+
+
+@pytest.fixture(scope="module")
+def st():
+    import gym_simpletetris_b200 as st
+
+    assert torch.cuda.is_available()
+    return st
+
+
+# ---- single-env facade (st_host_* ABI) vs fixtures generated from the unmodified reference ----------
+@pytest.mark.parametrize("key", ROLL.keys())
+def test_facade_rollout_matches_reference_fixture(st, key):
+    g = lambda f: ROLL.get(key, f)
+    env = st.make("SimpleTetris-v0", **ROLL.kwargs(key))
+    env.engine.set_pieces(g("pieces"))
+    resets = [digest(env.reset())]
+    for t, a in enumerate(g("actions")):
+        obs, r, d, info = env.step(int(a))
+        assert r == g("reward")[t], (key, t)
+        assert d == bool(g("done")[t]), (key, t)
+        assert info_row(info) == g("info")[t].tolist(), (key, t)
+        assert digest(obs) == g("digest")[t], (key, t)
+        if d:
+            resets.append(digest(env.reset()))
+    assert resets == g("reset_digest").tolist()
+    env.close()
+
+
+@pytest.mark.parametrize("key", SCEN.keys())
+def test_facade_scenario_matches_reference_fixture(st, key):
+    g = lambda f: SCEN.get(key, f)
+    env = st.make("SimpleTetris-v0", **SCEN.kwargs(key))
+    env.engine.set_pieces(g("pieces"))
+    assert digest(env.reset()) == g("reset_digest")[0]
+    env.engine.board = g("board")
+    for t, a in enumerate(g("actions")):
+        obs, r, d, info = env.step(int(a))
+        assert r == g("reward")[t], (key, t)
+        assert d == bool(g("done")[t]), (key, t)
+        assert info_row(info) == g("info")[t].tolist(), (key, t)
+        assert digest(obs) == g("digest")[t], (key, t)
+        e = env.engine
+        assert [e.anchor[0], e.anchor[1], e._lock_delay, e.piece_height] == g("anchor")[t].tolist(), (key, t)
+    assert np.array_equal(env.engine.board.astype(np.uint8), g("final_board"))
+    env.close()
+
+
+# ---- VecEnv (device-pointer ABI) vs the oracle on the same Philox streams ------------------------------
+def run_vec(st, n, acts, seed=0, env_id_base=0, per_step_obs=False, **kw):
+    env = st.VecEnv(n, device="cuda:0", seed=seed, env_id_base=env_id_base, **kw)
+    obs0 = env.reset().cpu().numpy().copy()
+    rew, don, inf, obs_t = [], [], [], []
+    for t in range(acts.shape[0]):
+        obs, r, d, info = env.step(torch.from_numpy(acts[t]).cuda())
+        rew.append(r.cpu().numpy().copy())
+        don.append(d.cpu().numpy().astype(np.uint8))
+        inf.append(env.info_buf.cpu().numpy()[:, INFO13].copy())
+        if per_step_obs:
+            obs_t.append(obs.cpu().numpy().copy())
+    assert env.poll_errors() == 0
+    return dict(obs0=obs0, obs=obs.cpu().numpy().reshape(n, -1).copy(), reward=np.stack(rew), done=np.stack(don),
+                info=np.stack(inf), obs_t=obs_t, env=env)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_vecenv_matches_oracle(st, name):
+    from oracle.oracle import rollout
+
+    kw = CASES[name]
+    image = kw.get("obs_type", "ram") != "ram"
+    n, T = (37, 150) if image else (261, 400)  # ragged: not a multiple of the 8 envs per CTA
+    acts = np.random.RandomState(11).randint(0, 7, (T, n)).astype(np.uint8)
+    got = run_vec(st, n, acts, seed=1234, env_id_base=5, **kw)
+    okw = {k: v for k, v in kw.items() if k != "extend_dims"}
+    want = rollout(n, acts, seed=1234, env_id_base=5, want_info=True, **okw)
+    assert want["error"] == 0
+    assert np.array_equal(got["reward"], want["reward"])
+    assert np.array_equal(got["done"], want["done"])
+    assert np.array_equal(got["info"], want["info"])
+    assert np.array_equal(got["obs"], want["obs"])
+    assert not got["obs0"].any() if not image else set(np.unique(got["obs0"])) <= {0.0, 128.0}
+
+
+@pytest.mark.parametrize("name", ["C2_ram_step_adv", "narrow4_adv_step", "C5a_rgb", "w20h40_gray", "w7h9_odd_gray"])
+def test_vecenv_every_step_obs_matches_oracle_env(st, name):
+    """Per-step observation bytes (not only the last step), envs driven one by one through OracleEnv."""
+    from oracle.oracle import OracleEnv
+
+    kw = CASES[name]
+    n, T = 9, 120
+    acts = np.random.RandomState(3).randint(0, 7, (T, n)).astype(np.uint8)
+    got = run_vec(st, n, acts, seed=77, per_step_obs=True, **kw)
+    for e in range(n):
+        o = OracleEnv(seed=77, env_id=e, **kw)
+        o.reset()
+        for t in range(T):
+            obs, r, d, info = o.step(int(acts[t, e]))
+            if d:
+                obs = o.reset()
+            assert np.array_equal(got["obs_t"][t][e], obs), (name, e, t)
+            assert got["reward"][t, e] == r and got["done"][t, e] == d
+
+
+def test_step_many_equals_repeated_step(st):
+    kw = dict(width=5, height=12, lock_delay=2, step_reset=True, reward_step=True, advanced_clears=True)
+    n, T = 130, 96
+    acts = np.random.RandomState(9).randint(0, 7, (T, n)).astype(np.uint8)
+    a = run_vec(st, n, acts, seed=5, **kw)
+    env = st.VecEnv(n, device="cuda:0", seed=5, **kw)
+    env.reset()
+    obs, rew, don, info = env.step_many(torch.from_numpy(acts).cuda(), rollout_obs=True, rollout_info=True)
+    assert np.array_equal(rew.cpu().numpy(), a["reward"])
+    assert np.array_equal(don.cpu().numpy().astype(np.uint8), a["done"])
+    assert np.array_equal(obs[-1].cpu().numpy().reshape(n, -1), a["obs"])
+    assert np.array_equal(info["time"].cpu().numpy(), a["info"][:, :, 0])
+    sa, sb = a["env"].get_state(), env.get_state()
+    assert torch.equal(sa[0], sb[0]) and torch.equal(sa[1], sb[1])
+
+
+def test_sharding_is_invisible(st):
+    """Env e plays the same game whether it lives in one 96-env shard or in the second of two 48-env shards."""
+    kw = dict(reward_step=True, penalise_holes_increase=True)
+    T = 200
+    acts = np.random.RandomState(21).randint(0, 7, (T, 96)).astype(np.uint8)
+    whole = run_vec(st, 96, acts, seed=8, **kw)
+    lo = run_vec(st, 48, acts[:, :48].copy(), seed=8, env_id_base=0, **kw)
+    hi = run_vec(st, 48, acts[:, 48:].copy(), seed=8, env_id_base=48, **kw)
+    for f in ("reward", "done", "info"):
+        assert np.array_equal(whole[f], np.concatenate([lo[f], hi[f]], axis=1)), f
+    assert np.array_equal(whole["obs"], np.concatenate([lo["obs"], hi["obs"]], axis=0))
+
+
+def test_masked_reset_and_no_autoreset(st):
+    n = 16
+    env = st.VecEnv(n, device="cuda:0", seed=1, auto_reset=False)
+    env.reset()
+    hard = torch.full((n,), 2, dtype=torch.uint8, device="cuda")
+    for _ in range(40):
+        obs, r, d, info = env.step(hard)
+    assert bool(d.all()) and bool((r == -100).all())  # keeps re-locking after done
+    deaths = info["deaths"].clone()
+    mask = torch.zeros(n, dtype=torch.uint8)
+    mask[::2] = 1
+    before = env.obs.clone()
+    o = env.reset(mask)
+    assert bool((o[::2] == 0).all()) and torch.equal(o[1::2], before[1::2])
+    obs, r, d, info = env.step(hard)
+    assert not bool(d[::2].any()) and bool(d[1::2].all())
+    assert torch.equal(info["deaths"][::2], deaths[::2])  # deaths persist across reset (ref:306-315)
+    assert bool((info["time"][::2] == 1).all())
+
+
+def test_error_flags(st):
+    env = st.VecEnv(8, device="cuda:0")
+    env.step(torch.zeros(8, dtype=torch.uint8))
+    assert env.poll_errors() & 4  # step before reset
+    env.reset()
+    env.step(torch.full((8,), 9, dtype=torch.uint8))
+    assert env.poll_errors() == 2  # bad action -> idle + flag
+    env.set_piece_queue(np.zeros((8, 2), dtype=np.uint8))
+    for _ in range(30):
+        env.step(torch.full((8,), 2, dtype=torch.uint8))
+    assert env.poll_errors() & 1  # queue exhausted
+    single = st.make("SimpleTetris-v0")
+    with pytest.raises(TypeError):
+        single.step(0)
+    single.reset()
+    with pytest.raises(KeyError):
+        single.step(7)
+
+
+def test_observe_matches_step_obs(st):
+    for kw in (dict(), dict(obs_type="grayscale"), dict(obs_type="rgb", width=20, height=40)):
+        env = st.VecEnv(21, device="cuda:0", seed=4, auto_reset=False, lock_delay=1, **kw)
+        env.reset()
+        rs = np.random.RandomState(0)
+        for _ in range(60):
+            obs, r, d, _ = env.step(torch.from_numpy(rs.randint(0, 7, 21).astype(np.uint8)))
+            live = ~d
+            assert torch.equal(env.observe(True)[live], obs[live])
+        boards, _ = env.get_state()
+        if kw.get("obs_type", "ram") == "ram":
+            assert torch.equal(env.observe(False), boards.float())
+
+
+# ---- BASELINE.json sizes: size-independent properties ---------------------------------------------------
+@pytest.mark.parametrize("n,kw", [
+    (4096, dict(reward_step=True, advanced_clears=True)),
+    (65536, dict(penalise_height_increase=True, penalise_holes_increase=True, lock_delay=3, step_reset=True)),
+    (65536, dict(width=20, height=40)),
+])
+def test_full_size_ram_properties(st, n, kw):
+    from oracle.oracle import OracleEnv
+
+    env = st.VecEnv(n, device="cuda:0", seed=2, **kw)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    T = 120
+    sample = torch.arange(0, n, n // 16, device="cuda")
+    episodes = torch.zeros(n, dtype=torch.int64, device="cuda")
+    trace = []
+    for t in range(T):
+        a = torch.randint(0, 7, (n,), dtype=torch.uint8, device="cuda", generator=g)
+        obs, r, d, info = env.step(a)
+        episodes += d
+        assert bool((r[d] == -100).all())
+        trace.append((a[sample].cpu().numpy(), obs[sample].cpu().numpy().copy(), r[sample].cpu().numpy().copy(),
+                      d[sample].cpu().numpy().copy()))
+    boards, sc = env.get_state()
+    # the returned obs is the locked board plus the active piece, except right after an auto-reset (empty)
+    shown = env.observe(True)
+    assert torch.equal(obs[~d], shown[~d]) and not bool(obs[d].any())
+    assert torch.equal(sc[:, 10].long(), episodes)  # deaths counter == number of done flags seen
+    assert bool((sc[:, 11:18].sum(1) >= episodes + 1).all())  # every (re)set spawns a piece
+    assert env.poll_errors() == 0
+    assert env.episode_stats(reduce=False)["episodes"] == int(episodes.sum())
+    # oracle re-run of a strided sample of envs at this size (same Philox streams, same global ids)
+    for k, e in enumerate(sample.tolist()):
+        o = OracleEnv(seed=2, env_id=e, **kw)
+        o.reset()
+        for t in range(T):
+            want, r, dn, _ = o.step(int(trace[t][0][k]))
+            if dn:
+                want = o.reset()
+            assert np.array_equal(trace[t][1][k], want) and trace[t][2][k] == r and trace[t][3][k] == dn, (e, t)
+
+
+@pytest.mark.parametrize("n,kw", [
+    (32768, dict(obs_type="grayscale", extend_dims=True, high_scoring=True)),
+    (16384, dict(obs_type="rgb")),
+])
+def test_full_size_image_properties(st, n, kw):
+    """Image obs at scale: only {0,128,190}; 190-pixels = block area x displayed cells; border/gap pixels fixed."""
+    env = st.VecEnv(n, device="cuda:0", seed=6, **kw)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for t in range(25):
+        obs, r, d, info = env.step(torch.randint(0, 7, (n,), dtype=torch.uint8, device="cuda", generator=g))
+    ram = st.VecEnv(n, device="cuda:0", seed=6, **{**kw, "obs_type": "ram", "extend_dims": False})
+    ram.state.copy_(env.state)
+    cells = ram.observe(True).sum(dim=(1, 2))
+    cells[d] = 0  # auto-reset envs show the empty board
+    flat = obs.reshape(n, -1)
+    ch = 3 if kw["obs_type"] == "rgb" else 1
+    assert bool(((flat == 0) | (flat == 128) | (flat == 190)).all())
+    assert torch.equal((flat == 190).sum(1).float(), cells * 9 * ch)  # 10x20 at 84: 3x3 blocks
+    assert bool(((flat == 0).sum(1) == 3735 * ch).all())  # border pixels

@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/sec of the batched SimpleTetris step path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--modes all|none|C3,C4,...]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one `st_step` launch over one batch of envs (action -> obs, reward, done, info, with
+in-kernel auto-reset).  Headline workload (BASELINE.json configs[1], "C2"): 4096 envs per GPU, 20x10 board,
+ram observations, reward_step + advanced_clears, uniform random actions already resident in HBM.
+Timing: CUDA events on the launching stream around every step, L2 flushed (256 MiB write) between timed
+steps, barrier + synchronize on both sides of the K steps, max over ranks.  `e2e` is the same metric through
+the host-buffer C ABI (`st_host_step`: pinned host actions in, obs/reward/done/info out, every step).
+`modes` carries the other BASELINE.json configs (C3, C4, C5a, C5b) measured the same way, each with its own
+roofline; `cpu_baseline` is the CPU oracle (a C port of the reference algorithm) on this box's host cores.
+`--impl reference` times that CPU port alone, on all host threads, on the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+# ---- workloads (BASELINE.json configs) ---------------------------------------------------------------
+WORKLOADS = {
+    "C2": dict(n=4096, kw=dict(reward_step=True, advanced_clears=True),
+               desc="C2: 4096 envs/GPU, 20x10, ram obs, reward_step+advanced_clears"),
+    "C3": dict(n=65536, kw=dict(penalise_height_increase=True, penalise_holes_increase=True, lock_delay=3,
+                                step_reset=True),
+               desc="C3: 65536 envs/GPU, 20x10, ram obs, penalise_height_increase+penalise_holes_increase, "
+                    "lock_delay=3, step_reset"),
+    "C4": dict(n=262144, kw=dict(obs_type="grayscale", extend_dims=True, high_scoring=True),
+               desc="C4: 262144 envs/GPU, grayscale 84x84x1 obs, high_scoring"),
+    "C5a": dict(n=131072, kw=dict(obs_type="rgb"),
+                desc="C5a: 131072 envs/GPU (the per-GPU share of 2^20 envs on 8 GPUs), rgb 84x84x3 obs"),
+    "C5b": dict(n=65536, kw=dict(width=20, height=40),
+                desc="C5b: 65536 envs/GPU, wide board 40x20 (H=40, W=20), ram obs"),
+}
+HEADLINE = "C2"
+L2_FLUSH_BYTES = 256 << 20
+
+
+def algorithmic_bytes(kw):
+    """obs_bytes (float32) + 2 * state_bytes + 6 (action 1, reward 4, done 1)."""
+    W, H = kw.get("width", 10), kw.get("height", 20)
+    ot = kw.get("obs_type", "ram")
+    obs = 4 * (W * H if ot == "ram" else 84 * 84 * (3 if ot == "rgb" else 1))
+    state = 60 + H * (2 if W <= 16 else 4)
+    return obs + 2 * state + 6
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+# ---- clocks sampling during the timed regions -----------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+        busy = [s for s in self.samples if self.max_mhz and s > 0.4 * self.max_mhz] or self.samples
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---- the GPU arm ---------------------------------------------------------------------------------------
+def time_workload(name, steps, warmup, rank, world, dist, burn_in=200):
+    """Device-timed steps of one workload on this rank's GPU.  Returns dict with per-rank numbers."""
+    import torch
+
+    import gym_simpletetris_b200 as st
+    from gym_simpletetris_b200 import native
+
+    wl = WORKLOADS[name]
+    n, kw = wl["n"], wl["kw"]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    env = st.VecEnv(n, device=dev, seed=0, env_id_base=rank * n, **kw)
+    env.reset()
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    burn = torch.randint(0, 7, (burn_in, n), dtype=torch.uint8, device=dev, generator=g)
+    image = kw.get("obs_type", "ram") != "ram"
+    if image:  # steady-state boards without writing burn_in images: step the same state through a ram twin
+        twin = st.VecEnv(n, device=dev, seed=0, env_id_base=rank * n, **{**kw, "obs_type": "ram", "extend_dims": False})
+        twin.state.copy_(env.state)
+        twin.step_many(burn)
+        env.state.copy_(twin.state)
+        del twin
+    else:
+        env.step_many(burn)
+    actions = torch.randint(0, 7, (warmup + steps, n), dtype=torch.uint8, device=dev, generator=g)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    for t in range(warmup):
+        env.step(actions[t])
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    launches0 = native.launch_count()
+    for t in range(steps):
+        flush.zero_()  # L2 flush between timed iterations (not timed)
+        ev[t][0].record()
+        env.step(actions[warmup + t])
+        ev[t][1].record()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    launches = native.launch_count() - launches0
+    per_step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(per_step_ms))
+    if world > 1:
+        tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+    assert env.poll_errors() == 0
+    stats = env.episode_stats(reduce=True)
+    B = algorithmic_bytes(kw)
+    peak, peak_src = measured_peak()
+    kernel_ms = statistics.mean(per_step_ms)
+    achieved = B * n / (kernel_ms * 1e-3) / 1e9
+    res = {
+        "workload": wl["desc"], "envs_per_gpu": n, "steps": steps,
+        "value": n * world * steps / (total_ms * 1e-3), "ms_per_step": total_ms / steps,
+        "ms_per_step_median_rank": statistics.median(per_step_ms),
+        "launches": launches, "episodes_all_ranks": stats["episodes"],
+        "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                     "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                     "kernel": f"st_main_kernel<{2 if kw.get('height', 20) > 31 else 1},"
+                               f"{ {'ram': 0, 'grayscale': 1, 'rgb': 2}[kw.get('obs_type', 'ram')] }>",
+                     "algorithmic_bytes_per_env_step": B, "env_steps_per_launch": n,
+                     "avg_launch_ms": round(kernel_ms, 6)},
+    }
+    del env, flush, actions
+    torch.cuda.empty_cache()
+    return res
+
+
+def time_e2e(name, steps, warmup, rank, world, dist):
+    """Same metric through the host-buffer C ABI: pinned host actions in, obs/reward/done/info out, every step."""
+    import ctypes as C
+
+    import torch
+
+    from gym_simpletetris_b200 import native
+
+    wl = WORKLOADS[name]
+    n, kw = wl["n"], wl["kw"]
+    L = native.lib()
+    base = dict(width=10, height=20, obs_type="ram", extend_dims=False, lock_delay=0, step_reset=False,
+                reward_step=False, penalise_height=False, penalise_height_increase=False, advanced_clears=False,
+                high_scoring=False, penalise_holes=False, penalise_holes_increase=False)
+    base.update(kw)
+    cfg = native.make_config(auto_reset=True, device=torch.cuda.current_device(), seed=0, env_id_base=rank * n, **base)
+    h = L.st_host_create(C.byref(cfg), n)
+    if not h:
+        raise RuntimeError("st_host_create: " + L.st_last_error().decode())
+    elems = int(L.st_obs_elems(C.byref(cfg)))
+    obs = torch.empty((n, elems), dtype=torch.float32).pin_memory()
+    reward = torch.empty(n, dtype=torch.float32).pin_memory()
+    done = torch.empty(n, dtype=torch.uint8).pin_memory()
+    info = torch.empty((n, native.ST_INFO_WORDS), dtype=torch.int32).pin_memory()
+    acts = torch.from_numpy(np.random.RandomState(7 + rank).randint(0, 7, (warmup + steps, n)).astype(np.uint8)).pin_memory()
+    native.check(L.st_host_reset(h, None, obs.data_ptr()), "st_host_reset")
+    step = lambda t: native.check(L.st_host_step(h, acts[t].data_ptr(), obs.data_ptr(), reward.data_ptr(),
+                                                 done.data_ptr(), info.data_ptr()), "st_host_step")
+    for t in range(warmup):
+        step(t)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for t in range(warmup, warmup + steps):
+        step(t)  # synchronous: returns when the results are in host memory
+    dt = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+    L.st_host_destroy(h)
+    d2h = n * (elems * 4 + 4 + 1 + 4 * native.ST_INFO_WORDS)
+    return {"value": n * world * steps / dt, "unit": "env-steps/s", "h2d_bytes_per_step": n,
+            "d2h_bytes_per_step": d2h, "ms_per_step": dt / steps * 1e3,
+            "api": "st_host_step (C ABI, pinned host buffers, sync per step)"}
+
+
+# ---- the CPU arm (oracle port of the reference algorithm) ---------------------------------------------------
+def cpu_vec_env(name, nthreads, n=None):
+    from oracle.oracle import OracleVecEnv
+
+    wl = WORKLOADS[name]
+    env = OracleVecEnv(n or wl["n"], seed=0, nthreads=nthreads, **wl["kw"])
+    env.reset()
+    return env
+
+
+def time_cpu(name, budget_s, nthreads, n=None):
+    """Bounded sample: whole vector steps of the workload until ~budget_s seconds of wall time are used."""
+    from oracle.oracle import max_threads
+
+    env = cpu_vec_env(name, nthreads, n)
+    rs = np.random.RandomState(3)
+    chunk, done_steps, t_used = 4, 0, 0.0
+    env.step_many(rs.randint(0, 7, (2, env.n)).astype(np.uint8))  # warm caches
+    while t_used < budget_s:
+        a = rs.randint(0, 7, (chunk, env.n)).astype(np.uint8)
+        t0 = time.perf_counter()
+        env.step_many(a)
+        t_used += time.perf_counter() - t0
+        done_steps += chunk
+        chunk = min(chunk * 2, 4096)
+    threads = nthreads if nthreads > 0 else max_threads()
+    return {"value": env.n * done_steps / t_used, "unit": "env-steps/s", "cores": threads, "kind": "port",
+            "sample": f"{env.n} envs x {done_steps} vector steps of the {name} workload in {t_used:.1f} s, "
+                      f"oracle/st_oracle.c (C port of the reference algorithm), OpenMP {threads} threads",
+            "host_cores": os.cpu_count()}
+
+
+def reference_arm(args):
+    """`--impl reference`: the CPU port on all host threads, K vector steps of the headline workload."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return  # other ranks exit 0 without work
+    from oracle.oracle import max_threads
+
+    wl = WORKLOADS[HEADLINE]
+    n = wl["n"] * args.gpus
+    env = cpu_vec_env(HEADLINE, 0, n)
+    rs = np.random.RandomState(3)
+    acts = rs.randint(0, 7, (args.warmup + args.steps, n)).astype(np.uint8)
+    for t in range(args.warmup):
+        env.step(acts[t])
+    t0 = time.perf_counter()
+    for t in range(args.warmup, args.warmup + args.steps):
+        env.step(acts[t])
+    dt = time.perf_counter() - t0
+    v = n * args.steps / dt
+    threads = max_threads()
+    line = {
+        "impl": "reference", "metric": "env-steps/sec", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["desc"].replace("/GPU", f" x {args.gpus}"), "envs": n,
+                   "note": "CPU: oracle/st_oracle.c, a C restatement of the reference's dense float64 algorithm "
+                           "(the reference itself is pure Python and does not travel to the GPU box)"},
+        "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port",
+                         "sample": f"{n} envs x {args.steps} vector steps, OpenMP {threads} threads",
+                         "host_cores": os.cpu_count()},
+        "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--modes", default="all", help="extra workloads to report in `modes`: all | none | C3,C4,...")
+    ap.add_argument("--mode-steps", type=int, default=30)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="0 skips the cpu_baseline leg")
+    ap.add_argument("--workload", default=HEADLINE, choices=list(WORKLOADS),
+                    help="headline workload (default C2 = BASELINE.json configs[1]); others are for profiling")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if world != args.gpus and rank == 0:
+        print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    head = time_workload(args.workload, args.steps, args.warmup, rank, world, dist)
+    e2e = None if args.no_e2e else time_e2e(args.workload, min(args.steps, 200), args.warmup, rank, world, dist)
+    modes = {}
+    names = [] if args.modes == "none" else ([k for k in WORKLOADS if k != args.workload] if args.modes == "all"
+                                              else args.modes.split(","))
+    for nm in names:
+        r = time_workload(nm, args.mode_steps, max(3, min(args.warmup, 5)), rank, world, dist)
+        r["e2e"] = time_e2e(nm, 5, 3, rank, world, dist) if WORKLOADS[nm]["n"] * algorithmic_bytes(WORKLOADS[nm]["kw"]) < (2 << 30) else None
+        modes[nm] = r
+    clocks = sampler.stop()
+
+    cpu = None
+    if rank == 0 and world == 1 and args.cpu_seconds > 0:
+        cpu = time_cpu(args.workload, args.cpu_seconds, 0)
+        cpu["single_thread"] = time_cpu(args.workload, min(3.0, args.cpu_seconds), 1)["value"]
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {
+        "metric": "env-steps/sec", "value": head["value"], "unit": "env-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": head["workload"], "envs_per_gpu": head["envs_per_gpu"],
+                   "actions": "uniform iid over 0..6, uint8, resident in HBM; boards in steady state (200 burn-in steps)",
+                   "obs": "float32, as the reference returns", "info": "written every step", "auto_reset": True,
+                   "l2": "flushed between timed steps (256 MiB write, not timed)",
+                   "timing": "CUDA events per step on the launching stream, summed; max over ranks"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": head["launches"], "roofline": head["roofline"],
+        "cpu_baseline": cpu, "modes": modes,
+    }
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -197,3 +197,54 @@ def rollout(num_envs, actions, *, width=10, height=20, obs_type="ram", lock_dela
                        obs.ctypes.data if want_obs else None, reward.ctypes.data, done.ctypes.data,
                        info.ctypes.data if want_info else None, int(bool(auto_reset)), int(nthreads))
     return {"obs": obs, "reward": reward, "done": done, "info": info, "error": err}
+
+
+class OracleVecEnv:
+    """N persistent oracle envs with VecEnv semantics (auto-reset), stepped by or_rollout over OpenMP threads.
+    CPU baseline / reference arm of bench.py, and a checker in tests."""
+
+    def __init__(self, num_envs, *, width=10, height=20, obs_type="ram", lock_delay=0, step_reset=False,
+                 seed=0, env_id_base=0, auto_reset=True, nthreads=0, extend_dims=False, **flags):
+        self._L = lib()
+        self.n, self.width, self.height = int(num_envs), width, height
+        self._ot = OBS_TYPES[obs_type]
+        self._args = (width, height, int(lock_delay), int(bool(step_reset)), _flags(flags), self._ot,
+                      int(seed) & (2**64 - 1), int(env_id_base))
+        self._auto, self._nt = int(bool(auto_reset)), int(nthreads)
+        self._envs = (C.c_void_p * self.n)(*[
+            self._L.or_create(width, height, int(lock_delay), int(bool(step_reset)), _flags(flags),
+                              int(seed) & (2**64 - 1), int(env_id_base) + i) for i in range(self.n)])
+        self.elems = self._L.or_obs_elems(width, height, self._ot)
+        self.obs = np.zeros((self.n, self.elems), dtype=np.float32)
+
+    def __del__(self):
+        for h in getattr(self, "_envs", []):
+            if h:
+                self._L.or_destroy(h)
+        self._envs = []
+
+    def reset(self):
+        for i, h in enumerate(self._envs):
+            self._L.or_reset(h, self._ot, self.obs[i].ctypes.data)
+        return self.obs
+
+    def step_many(self, actions, want_info=False):
+        """actions uint8 [T, N] -> (obs of last step [N, elems], reward [T,N], done [T,N], info [T,N,13]|None)"""
+        actions = np.ascontiguousarray(actions, dtype=np.uint8)
+        T = actions.shape[0]
+        reward = np.zeros((T, self.n), dtype=np.float32)
+        done = np.zeros((T, self.n), dtype=np.uint8)
+        info = np.zeros((T, self.n, 13), dtype=np.int32) if want_info else None
+        a = self._args
+        self._L.or_rollout(self._envs, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], self.n, T,
+                           actions.ctypes.data, self.obs.ctypes.data, reward.ctypes.data, done.ctypes.data,
+                           info.ctypes.data if want_info else None, self._auto, self._nt)
+        return self.obs, reward, done, info
+
+    def step(self, actions, want_info=False):
+        obs, r, d, i = self.step_many(np.asarray(actions, dtype=np.uint8).reshape(1, self.n), want_info)
+        return obs, r[0], d[0], (i[0] if want_info else None)
+
+
+def max_threads() -> int:
+    return int(lib().or_max_threads())

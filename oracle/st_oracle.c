@@ -501,7 +501,7 @@ API int or_rollout(OrEnv **envs, int W, int H, int lock_delay, int step_reset, c
     int err = 0;
     int elems = or_obs_elems(W, H, obs_type);
 #ifdef _OPENMP
-    if (nthreads > 0) omp_set_num_threads(nthreads);
+    omp_set_num_threads(nthreads > 0 ? nthreads : omp_get_num_procs());
 #endif
 #pragma omp parallel for schedule(static) reduction(| : err)
     for (int64_t i = 0; i < n; ++i) {
@@ -525,7 +525,7 @@ API int or_rollout(OrEnv **envs, int W, int H, int lock_delay, int step_reset, c
 API int or_max_threads(void)
 {
 #ifdef _OPENMP
-    return omp_get_max_threads();
+    return omp_get_num_procs();
 #else
     return 1;
 #endif

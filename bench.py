@@ -7,8 +7,9 @@
 One "step" = one `st_step` launch over one batch of envs (action -> obs, reward, done, info, with
 in-kernel auto-reset).  Headline workload (BASELINE.json configs[1], "C2"): 4096 envs per GPU, 20x10 board,
 ram observations, reward_step + advanced_clears, uniform random actions already resident in HBM.
-Timing: CUDA events on the launching stream around every step, L2 flushed (256 MiB write) between timed
-steps, barrier + synchronize on both sides of the K steps, max over ranks.  `e2e` is the same metric through
+Timing: the K steps are K kernel launches replayed from CUDA graphs, bracketed by one CUDA-event pair on the
+launching stream and by barrier + synchronize on both sides, max over ranks; inputs are larger than L2 (the
+steps rotate over enough replicas of the batch that every step's lines come from HBM).  `e2e` is the same metric through
 the host-buffer C ABI (`st_host_step`: pinned host actions in, obs/reward/done/info out, every step).
 `modes` carries the other BASELINE.json configs (C3, C4, C5a, C5b) measured the same way, each with its own
 roofline; `cpu_baseline` is the CPU oracle (a C port of the reference algorithm) on this box's host cores.
@@ -46,7 +47,7 @@ WORKLOADS = {
                 desc="C5b: 65536 envs/GPU, wide board 40x20 (H=40, W=20), ram obs"),
 }
 HEADLINE = "C2"
-L2_FLUSH_BYTES = 256 << 20
+L2_BYTES = 126 << 20
 
 
 def algorithmic_bytes(kw):
@@ -114,73 +115,94 @@ class ClockSampler:
 
 # ---- the GPU arm ---------------------------------------------------------------------------------------
 def time_workload(name, steps, warmup, rank, world, dist, burn_in=200):
-    """Device-timed steps of one workload on this rank's GPU.  Returns dict with per-rank numbers."""
+    """Device-timed steps of one workload on this rank's GPU.
+
+    L2 rule: the working set is made larger than L2 by rotating over R independent replicas of the batch
+    (step t runs on replica t % R; R * bytes-per-step >= 2.5 x the 126 MB L2), so every step's state and
+    observation lines come from / go to HBM.  The K steps are K launches of the step kernel, captured into
+    CUDA graphs (<= 500 launches each) so that the device, not the Python launch loop, is what is timed;
+    one CUDA-event pair brackets the K steps.
+    """
     import torch
 
     import gym_simpletetris_b200 as st
-    from gym_simpletetris_b200 import native
-
     wl = WORKLOADS[name]
     n, kw = wl["n"], wl["kw"]
     dev = torch.device("cuda", torch.cuda.current_device())
-    env = st.VecEnv(n, device=dev, seed=0, env_id_base=rank * n, **kw)
-    env.reset()
+    B = algorithmic_bytes(kw)
+    R = max(1, -(-int(2.5 * L2_BYTES) // (B * n)))
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
-    burn = torch.randint(0, 7, (burn_in, n), dtype=torch.uint8, device=dev, generator=g)
     image = kw.get("obs_type", "ram") != "ram"
-    if image:  # steady-state boards without writing burn_in images: step the same state through a ram twin
-        twin = st.VecEnv(n, device=dev, seed=0, env_id_base=rank * n, **{**kw, "obs_type": "ram", "extend_dims": False})
-        twin.state.copy_(env.state)
-        twin.step_many(burn)
-        env.state.copy_(twin.state)
-        del twin
-    else:
-        env.step_many(burn)
+    envs = []
+    for r in range(R):
+        env = st.VecEnv(n, device=dev, seed=r, env_id_base=rank * n, **kw)
+        env.reset()
+        burn = torch.randint(0, 7, (burn_in, n), dtype=torch.uint8, device=dev, generator=g)
+        if image:  # steady-state boards without writing burn_in images: step the same state through a ram twin
+            twin = st.VecEnv(n, device=dev, seed=r, env_id_base=rank * n,
+                             **{**kw, "obs_type": "ram", "extend_dims": False})
+            twin.state.copy_(env.state)
+            twin.step_many(burn)
+            env.state.copy_(twin.state)
+            del twin
+        else:
+            env.step_many(burn)
+        envs.append(env)
     actions = torch.randint(0, 7, (warmup + steps, n), dtype=torch.uint8, device=dev, generator=g)
-    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
-    for t in range(warmup):
-        env.step(actions[t])
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    launches0 = native.launch_count()
-    for t in range(steps):
-        flush.zero_()  # L2 flush between timed iterations (not timed)
-        ev[t][0].record()
-        env.step(actions[warmup + t])
-        ev[t][1].record()
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    launches = native.launch_count() - launches0
-    per_step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = float(sum(per_step_ms))
+    stream = torch.cuda.Stream(device=dev)
+    graphs = []
+    with torch.cuda.stream(stream):
+        for t in range(warmup):
+            envs[t % R].step(actions[t])
+        stream.synchronize()
+        t = 0
+        while t < steps:
+            chunk = min(500, steps - t)
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=stream):
+                for u in range(t, t + chunk):
+                    envs[u % R].step(actions[warmup + u])
+            graphs.append(gr)
+            t += chunk
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0.record(stream)
+        for gr in graphs:
+            gr.replay()
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+    total_ms = float(e0.elapsed_time(e1))
+    launches = steps  # one st_main_kernel launch per step (graph replays of the captured launches)
+    rank_ms = total_ms
     if world > 1:
         tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         total_ms = float(tt.item())
-    assert env.poll_errors() == 0
-    stats = env.episode_stats(reduce=True)
-    B = algorithmic_bytes(kw)
+    stats = {"episodes": 0}
+    for env in envs:
+        assert env.poll_errors() == 0
+        stats["episodes"] += env.episode_stats(reduce=True)["episodes"]
     peak, peak_src = measured_peak()
-    kernel_ms = statistics.mean(per_step_ms)
+    kernel_ms = rank_ms / steps
     achieved = B * n / (kernel_ms * 1e-3) / 1e9
     res = {
-        "workload": wl["desc"], "envs_per_gpu": n, "steps": steps,
+        "workload": wl["desc"], "envs_per_gpu": n, "steps": steps, "replicas": R,
         "value": n * world * steps / (total_ms * 1e-3), "ms_per_step": total_ms / steps,
-        "ms_per_step_median_rank": statistics.median(per_step_ms),
         "launches": launches, "episodes_all_ranks": stats["episodes"],
         "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
                      "kernel": f"st_main_kernel<{2 if kw.get('height', 20) > 31 else 1},"
-                               f"{ {'ram': 0, 'grayscale': 1, 'rgb': 2}[kw.get('obs_type', 'ram')] }>",
+                               f"{ {'ram': 0, 'grayscale': 1, 'rgb': 2}[kw.get('obs_type', 'ram')] },STEP>",
                      "algorithmic_bytes_per_env_step": B, "env_steps_per_launch": n,
                      "avg_launch_ms": round(kernel_ms, 6)},
     }
-    del env, flush, actions
+    del envs, actions, graphs
     torch.cuda.empty_cache()
     return res
 
@@ -360,8 +382,10 @@ def main():
         "config": {"workload": head["workload"], "envs_per_gpu": head["envs_per_gpu"],
                    "actions": "uniform iid over 0..6, uint8, resident in HBM; boards in steady state (200 burn-in steps)",
                    "obs": "float32, as the reference returns", "info": "written every step", "auto_reset": True,
-                   "l2": "flushed between timed steps (256 MiB write, not timed)",
-                   "timing": "CUDA events per step on the launching stream, summed; max over ranks"},
+                   "l2": f"inputs larger than L2: step t runs on replica t % {head['replicas']} of the batch "
+                         f"({head['replicas']} x {head['envs_per_gpu']} envs, >= 2.5 x 126 MB per rotation)",
+                   "timing": "K step-kernel launches replayed from CUDA graphs, one CUDA-event pair on the "
+                             "launching stream around them, barrier + synchronize on both sides; max over ranks"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": head["launches"], "roofline": head["roofline"],
         "cpu_baseline": cpu, "modes": modes,
     }

@@ -2,26 +2,32 @@
 //
 // What the reference does in tetris_env.py:10-335 + 397-433 (cited as ref:LINE) on a dense float64
 // (W,H) array is done here on a row bitboard held in registers: lane l of the env's warp owns row l
-// (and row l+32 when H > 31).  Collision for EVERY anchor height at once is an AND of shifted piece
-// row masks followed by one warp OR-reduction (REDUX), so soft drop, hard drop, gravity and the
-// grounded test all read the same mask.  Line clear is compare-to-full + ballot + shuffle compaction,
-// holes are a shuffle prefix-OR + popc, height is popc of a ballot.  Control flow is uniform per warp
-// (one env), so the rare lock / spawn / reset branches cost nothing when they are not taken.
-// Observations: ram is expanded by the env's own warp from a 128-byte smem staging row with 16-byte
-// stores; 84x84 images are written by the whole CTA (8 envs) with every thread owning a fixed
-// 16-byte column slot, so a warp store covers 512 contiguous bytes.
+// (and row l+32 when H > 31).  A row register is "widened": board column x sits at bit x+4, bits 0..3
+// and every bit from W+4 up are permanently-set WALL bits.  A piece row mask shifted to column x is
+// then tested with one AND per row — walls need no separate test, and rows above the board have no lane,
+// so they are skipped for board AND walls exactly like ref:32-33.
+// Four ballots (one per piece row) give the collision answer for EVERY anchor height at once, so soft
+// drop, hard drop (one ctz), gravity and the grounded test all read the same mask.  Line clear is
+// compare-to-all-ones + ballot + shuffle compaction, holes are a shuffle prefix-OR + popc, height is popc
+// of a ballot.  Control flow is uniform per warp (one env), so the lock / spawn / reset branches cost
+// nothing when they are not taken.
+// Observations: ram is expanded by the env's own warp from a smem staging row with 16-byte stores;
+// 84x84 images are written by the whole CTA (8 envs) with every thread owning a fixed 16-byte column
+// slot, so a warp store covers 512 contiguous bytes.
 #include "st_internal.h"
 
 namespace st {
 
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int OFF = 4;  // board column x lives at bit x + OFF of a widened row
+
 // ---------------------------------------------------------------------------------------------
-// Piece table: 7 pieces x 4 rotations.  Entry = 7x7 bit grid, bit (j+3)*7 + (i+3) for cell offset
-// (i,j) from the anchor (ref:10-19), rotation r = r applications of (i,j)->(j,-i) (ref:22-26).
+// Piece table: 7 pieces x 4 rotations (ref:10-19; rotation r = r applications of (i,j)->(j,-i), ref:22-26).
+// Entry: bits 0..27 = four 7-bit row masks (row t is piece row j = minj + t; bit i+3 = cell offset i),
+//        bits 32..35 = minj + 3, bits 36..39 = maxj + 3.
 // ---------------------------------------------------------------------------------------------
 struct PieceTab {
-    unsigned long long m[28];
-    signed char minj[28];
-    signed char maxj[28];
+    unsigned long long e[28];
 };
 
 constexpr PieceTab make_piece_tab()
@@ -40,17 +46,16 @@ constexpr PieceTab make_piece_tab()
         int c[4][2] = {};
         for (int k = 0; k < 4; ++k) { c[k][0] = base[id][k][0]; c[k][1] = base[id][k][1]; }
         for (int r = 0; r < 4; ++r) {
-            unsigned long long m = 0;
             int mn = 0, mx = 0;
             for (int k = 0; k < 4; ++k) {
-                int i = c[k][0], j = c[k][1];
-                m |= 1ull << ((j + 3) * 7 + (i + 3));
-                mn = j < mn ? j : mn;
-                mx = j > mx ? j : mx;
+                mn = c[k][1] < mn ? c[k][1] : mn;
+                mx = c[k][1] > mx ? c[k][1] : mx;
             }
-            t.m[id * 4 + r] = m;
-            t.minj[id * 4 + r] = (signed char)mn;
-            t.maxj[id * 4 + r] = (signed char)mx;
+            unsigned long long m = 0;
+            for (int k = 0; k < 4; ++k) m |= 1ull << ((c[k][1] - mn) * 7 + (c[k][0] + 3));
+            m |= (unsigned long long)(mn + 3) << 32;
+            m |= (unsigned long long)(mx + 3) << 36;
+            t.e[id * 4 + r] = m;
             for (int k = 0; k < 4; ++k) { int i = c[k][0], j = c[k][1]; c[k][0] = j; c[k][1] = -i; }
         }
     }
@@ -59,76 +64,47 @@ constexpr PieceTab make_piece_tab()
 
 __constant__ PieceTab c_tab = make_piece_tab();
 
-constexpr unsigned FULL = 0xffffffffu;
-
-// ---------------------------------------------------------------------------------------------
-// Piece rows at column x.  Row t is piece row j = minj + t (rows past maxj are empty).
-//   mb[t]   in-board cells of that row as a board-row mask
-//   wall    bit t: that row has a cell at X < 0 or X >= W   (ref:34 wall test)
-// ---------------------------------------------------------------------------------------------
+// Piece rows at column x, as widened-row masks (cell X at bit X + OFF; x + 1 >= 0 since x >= -1).
+template <typename RowT>
 struct PieceRows {
-    uint32_t mb[4];
-    uint32_t wall;
+    RowT m[4];
     int minj, maxj;
 };
 
-__device__ __forceinline__ PieceRows piece_rows(int id, int rot, int x, int W, uint32_t fullmask)
+template <typename RowT>
+__device__ __forceinline__ PieceRows<RowT> piece_rows(int id, int rot, int x)
 {
-    const int s = id * 4 + rot;
-    const unsigned long long m = c_tab.m[s];
-    PieceRows pr;
-    pr.minj = c_tab.minj[s];
-    pr.maxj = c_tab.maxj[s];
-    pr.wall = 0;
+    const unsigned long long e = c_tab.e[id * 4 + rot];
+    const uint32_t lo = (uint32_t)e, hi = (uint32_t)(e >> 32);
+    PieceRows<RowT> pr;
+    pr.minj = (int)(hi & 15u) - 3;
+    pr.maxj = (int)((hi >> 4) & 15u) - 3;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        const int j = pr.minj + t;  // <= 3 because minj <= 0
-        const uint32_t m7 = (uint32_t)(m >> ((j + 3) * 7)) & 127u;
-        const uint32_t mb = x >= 3 ? (m7 << (x - 3)) : (m7 >> (3 - x));
-        const int lo = x - 3 + (__ffs((int)m7) - 1);
-        const int hi = x - 3 + (31 - __clz((int)m7));
-        const uint32_t wall = (m7 != 0u) && (lo < 0 || hi >= W);
-        pr.mb[t] = mb & fullmask;
-        pr.wall |= wall << t;
-    }
+    for (int t = 0; t < 4; ++t) pr.m[t] = (RowT)((lo >> (7 * t)) & 127u) << (x + 1);
     return pr;
 }
 
 template <int RPL> struct CMask { using type = uint32_t; };
 template <> struct CMask<2> { using type = unsigned long long; };
 
-__device__ __forceinline__ uint32_t warp_or(uint32_t v) { return __reduce_or_sync(FULL, v); }
-__device__ __forceinline__ unsigned long long warp_or(unsigned long long v)
-{
-    uint32_t lo = __reduce_or_sync(FULL, (uint32_t)v);
-    uint32_t hi = __reduce_or_sync(FULL, (uint32_t)(v >> 32));
-    return ((unsigned long long)hi << 32) | lo;
-}
 __device__ __forceinline__ int ctz(uint32_t v) { return __ffs((int)v) - 1; }
 __device__ __forceinline__ int ctz(unsigned long long v) { return __ffsll((long long)v) - 1; }
 
 // Collision mask over anchor heights: bit y' set <=> is_occupied(shape, (x, y'), board) (ref:29-36).
-// Rows with Y < 0 have no lane, so they are skipped for board AND walls, exactly like ref:32-33.
-template <int RPL>
-__device__ __forceinline__ typename CMask<RPL>::type collision_mask(const uint32_t (&row)[RPL], const PieceRows &pr,
-                                                                    int H, int lane)
+template <int RPL, typename RowT>
+__device__ __forceinline__ typename CMask<RPL>::type collision_mask(const RowT (&row)[RPL], const PieceRows<RowT> &pr, int H)
 {
     using M = typename CMask<RPL>::type;
-    constexpr int BITS = 32 * RPL;
     M c = 0;
 #pragma unroll
     for (int k = 0; k < RPL; ++k) {
-        const int Y = lane + 32 * k;
-        if (Y < H) {
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int yp = Y - (pr.minj + t);
-                const bool hit = ((pr.wall >> t) & 1u) || ((pr.mb[t] & row[k]) != 0u);
-                if (hit && yp >= 0 && yp < BITS) c |= (M)1 << yp;
-            }
+        for (int t = 0; t < 4; ++t) {
+            const M b = __ballot_sync(FULL, (pr.m[t] & row[k]) != 0);  // bit l: board row l+32k meets piece row t
+            const int sh = pr.minj + t - 32 * k;                         // anchor y' = row - (minj + t)
+            c |= sh >= 0 ? (b >> sh) : (b << -sh);
         }
     }
-    c = warp_or(c);
     int fl = H - pr.maxj;  // anchors whose lowest cell is at or below the floor (ref:34 `y >= board.shape[1]`)
     fl = fl < 0 ? 0 : fl;
     c |= ~(M)0 << fl;
@@ -185,68 +161,56 @@ __device__ __forceinline__ int spawn_piece(int &sw, int lane, const Params &p, l
 }
 
 // Rows [0, fr] shift down by one (row 0 becomes empty): removal of full row `fr` (ref:205-216).
-template <int RPL>
-__device__ __forceinline__ void remove_row(uint32_t (&row)[RPL], int fr, int lane)
+template <int RPL, typename RowT>
+__device__ __forceinline__ void remove_row(RowT (&row)[RPL], int fr, int lane, RowT walls)
 {
-    if (RPL == 1) {
-        const uint32_t up = __shfl_up_sync(FULL, row[0], 1);
-        if (lane <= fr) row[0] = lane ? up : 0u;
-    } else {
-        const uint32_t up0 = __shfl_up_sync(FULL, row[0], 1);
-        const uint32_t up1 = __shfl_up_sync(FULL, row[RPL - 1], 1);
-        const uint32_t last0 = __shfl_sync(FULL, row[0], 31);
+    const RowT up0 = __shfl_up_sync(FULL, row[0], 1);
+    if (RPL == 2) {
+        const RowT up1 = __shfl_up_sync(FULL, row[RPL - 1], 1);
+        const RowT last0 = __shfl_sync(FULL, row[0], 31);
         if (lane + 32 <= fr) row[RPL - 1] = lane ? up1 : last0;
-        if (lane <= fr) row[0] = lane ? up0 : 0u;
     }
+    if (lane <= fr) row[0] = lane ? up0 : walls;
 }
 
-// _count_holes (ref:218-220): empty cells with a filled cell above them in the same column.
-template <int RPL>
-__device__ __forceinline__ int count_holes(const uint32_t (&row)[RPL], int H, uint32_t fullmask, int lane)
+// _count_holes (ref:218-220): empty cells with a filled cell above them in the same column.  Wall bits are
+// set in every row, so `above & ~row` is zero on them without any masking.
+template <int RPL, typename RowT>
+__device__ __forceinline__ int count_holes(const RowT (&row)[RPL], int H, int lane)
 {
     int cnt = 0;
-    uint32_t carry = 0;  // OR of all rows of the previous 32-row block
+    RowT carry = 0;  // OR of all rows of the previous 32-row block
 #pragma unroll
     for (int k = 0; k < RPL; ++k) {
-        uint32_t v = row[k];
+        RowT v = row[k];
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(FULL, v, d);
+            const RowT t = __shfl_up_sync(FULL, v, d);
             if (lane >= d) v |= t;
         }
-        uint32_t above = __shfl_up_sync(FULL, v, 1);
+        RowT above = __shfl_up_sync(FULL, v, 1);
         if (lane == 0) above = 0;
         above |= carry;
-        if (lane + 32 * k < H) cnt += __popc(above & ~row[k] & fullmask);
+        if (lane + 32 * k < H) cnt += sizeof(RowT) == 8 ? __popcll(above & ~row[k]) : __popc((uint32_t)(above & ~row[k]));
         if (k + 1 < RPL) carry |= __shfl_sync(FULL, v, 31);
     }
     return __reduce_add_sync(FULL, cnt);
 }
 
-template <int RPL>
-__device__ __forceinline__ int nonempty_rows(const uint32_t (&row)[RPL])
-{
-    int n = 0;
-#pragma unroll
-    for (int k = 0; k < RPL; ++k) n += __popc(__ballot_sync(FULL, row[k] != 0u));
-    return n;
-}
-
-// The piece's cells on this lane's rows (ref:323-327 _set_piece: in-bounds cells only).
-template <int RPL>
-__device__ __forceinline__ void piece_on_rows(uint32_t (&pm)[RPL], const PieceRows &pr, int y, int lane)
+// The piece's cells on this lane's rows (ref:323-327 _set_piece; out-of-board cells land on wall bits).
+template <int RPL, typename RowT>
+__device__ __forceinline__ void piece_on_rows(RowT (&pm)[RPL], const PieceRows<RowT> &pr, int y, int lane)
 {
 #pragma unroll
     for (int k = 0; k < RPL; ++k) {
         const int t = lane + 32 * k - y - pr.minj;
-        uint32_t m = 0;
+        RowT m = 0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) m = (t == q) ? pr.mb[q] : m;
+        for (int q = 0; q < 4; ++q) m = (t == q) ? pr.m[q] : m;
         pm[k] = m;
     }
 }
 
-// Warp-uniform engine state (the scalars live in `sw`, one word per lane, between uses).
 struct Piece {
     int id, rot, x, y;
 };
@@ -263,26 +227,92 @@ __device__ __forceinline__ int get(int sw, int idx) { return __shfl_sync(FULL, s
 
 // clear() (ref:306-315): zero the per-episode counters, spawn, empty board.  The lock-delay counter,
 // deaths and shape_counts persist.
-template <int RPL>
-__device__ __forceinline__ void engine_clear(uint32_t (&row)[RPL], int &sw, Piece &pc, int lane, const Params &p,
-                                             long long e, int &errbits)
+template <int RPL, typename RowT>
+__device__ __forceinline__ void engine_clear(RowT (&row)[RPL], int &sw, Piece &pc, int lane, const Params &p,
+                                             long long e, int &errbits, RowT walls)
 {
     if (lane >= 2 && lane <= 6) sw = 0;  // time, score, lines_cleared, holes, piece_height
     pc.id = spawn_piece(sw, lane, p, e, errbits);
     pc.rot = 0; pc.x = p.W / 2; pc.y = 0;
 #pragma unroll
-    for (int k = 0; k < RPL; ++k) row[k] = 0;
+    for (int k = 0; k < RPL; ++k) row[k] = walls;
+}
+
+// The lock branch of TetrisEngine.step (ref:262-299), out of line: taken on ~1/5 of the steps.
+template <int RPL, typename RowT>
+__device__ __forceinline__ void engine_lock(RowT (&row)[RPL], int &sw, Piece &pc, PieceRows<RowT> &pr, int lane,
+                                         const Params &p, long long e, int &reward, int &done, int &errbits, RowT walls)
+{
+    const int H = p.H;
+    RowT pm[RPL];
+    piece_on_rows<RPL, RowT>(pm, pr, pc.y, lane);
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) row[k] |= pm[k];  // _set_piece(True) ref:263
+    // _clear_lines (ref:205-216): a full row has every bit set (walls included)
+    unsigned long long full = 0;
+#pragma unroll
+    for (int k = 0; k < RPL; ++k)
+        full |= (unsigned long long)__ballot_sync(FULL, (lane + 32 * k < H) && row[k] == ~(RowT)0) << (32 * k);
+    const int k_cleared = __popcll(full);
+    if (k_cleared) {
+        unsigned long long f = full;
+        while (f) {  // top-most full row first; rows below it keep their index
+            const int fr = __ffsll((long long)f) - 1;
+            f &= f - 1;
+            remove_row<RPL, RowT>(row, fr, lane, walls);
+        }
+        if (lane == 4) sw += k_cleared;  // lines_cleared (ref:213)
+    }
+    // line-clear reward / score (ref:266-275)
+    int dscore;
+    if (p.adv_clears) {
+        const int kk = k_cleared > 4 ? 4 : k_cleared;
+        dscore = kk == 0 ? 0 : kk == 1 ? 40 : kk == 2 ? 100 : kk == 3 ? 300 : 1200;
+        reward += (dscore * 5) / 2;  // 2.5 * {0,40,100,300,1200} is integral
+    } else if (p.high_scoring) {
+        dscore = k_cleared;
+        reward += 1000 * k_cleared;
+    } else {
+        dscore = k_cleared;
+        reward += 100 * k_cleared;
+    }
+    if (lane == 3) sw += dscore;
+    const int old_holes = get(sw, 5);
+    const int holes = count_holes<RPL, RowT>(row, H, lane);  // ref:278,284
+    put(sw, lane, 5, holes);
+    int nonempty = 0;
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) nonempty += __popc(__ballot_sync(FULL, row[k] != walls));
+    const bool top = (__ballot_sync(FULL, row[0] != walls) & 1u) != 0u;  // np.any(board[:,0]) ref:277
+    if (top) {
+        if (lane == 7) sw += 1;  // n_deaths (ref:279)
+        done = 1;
+        reward = -100;  // ref:281 overrides everything
+    } else {
+        if (p.pen_height) {  // ref:286-287: sum(np.any(board, axis=0)) = number of non-empty rows
+            reward -= nonempty;
+        } else if (p.pen_height_inc) {  // ref:288-292
+            const int ph = get(sw, 6);
+            if (nonempty > ph) reward -= 10 * (nonempty - ph);
+            put(sw, lane, 6, nonempty);
+        }
+        if (p.pen_holes) reward -= 5 * holes;  // ref:294-297
+        else if (p.pen_holes_inc) reward -= 5 * (holes - old_holes);
+        pc.id = spawn_piece(sw, lane, p, e, errbits);  // _new_piece ref:299
+        pc.rot = 0; pc.x = p.W / 2; pc.y = 0;
+        pr = piece_rows<RowT>(pc.id, 0, pc.x);
+    }
 }
 
 // TetrisEngine.step (ref:243-304).  Outputs reward/done and the display rows (board | piece, ref:301-302).
-template <int RPL>
-__device__ __forceinline__ void engine_step(uint32_t (&row)[RPL], uint32_t (&disp)[RPL], int &sw, Piece &pc, int action,
+template <int RPL, typename RowT>
+__device__ __forceinline__ void engine_step(RowT (&row)[RPL], RowT (&disp)[RPL], int &sw, Piece &pc, int action,
                                             int lane, const Params &p, long long e, int &reward, int &done,
-                                            int &errbits)
+                                            int &errbits, RowT walls)
 {
     using M = typename CMask<RPL>::type;
-    const int H = p.H, W = p.W;
-    reward = p.reward_step ? 1 : 0;  // ref:256
+    const int H = p.H;
+    reward = p.reward_step;  // ref:256
     done = 0;
     if (pc.id >= 7) {  // no piece yet: the reference would fail on shape None (ref:170-172,245)
         errbits |= 4;
@@ -298,12 +328,12 @@ __device__ __forceinline__ void engine_step(uint32_t (&row)[RPL], uint32_t (&dis
     if (action == 1) x2 += 1;
     if (action == 4) r2 = (r2 + 1) & 3;
     if (action == 5) r2 = (r2 + 3) & 3;
-    PieceRows pr = piece_rows(pc.id, r2, x2, W, p.fullmask);
-    M cm = collision_mask<RPL>(row, pr, H, lane);
+    PieceRows<RowT> pr = piece_rows<RowT>(pc.id, r2, x2);
+    M cm = collision_mask<RPL, RowT>(row, pr, H);
     const bool moved = (r2 != pc.rot) || (x2 != pc.x);
     if (moved && ((cm >> pc.y) & 1)) {  // blocked: stay (ref:41,46,64,69)
-        pr = piece_rows(pc.id, pc.rot, pc.x, W, p.fullmask);
-        cm = collision_mask<RPL>(row, pr, H, lane);
+        pr = piece_rows<RowT>(pc.id, pc.rot, pc.x);
+        cm = collision_mask<RPL, RowT>(row, pr, H);
     } else {
         pc.rot = r2; pc.x = x2;
     }
@@ -324,101 +354,45 @@ __device__ __forceinline__ void engine_step(uint32_t (&row)[RPL], uint32_t (&dis
 
     // ---- grounded -> lock delay -> lock (ref:259-299) ----
     if ((cm >> (y + 1)) & 1) {
-        ld = (ld + 1) % p.lock_mod;  // ref:175,260
-        if (ld == 0) {
-            uint32_t pm[RPL];
-            piece_on_rows<RPL>(pm, pr, y, lane);
-#pragma unroll
-            for (int k = 0; k < RPL; ++k) row[k] |= pm[k];  // _set_piece(True) ref:263
-            // _clear_lines (ref:205-216)
-            unsigned long long full = 0;
-#pragma unroll
-            for (int k = 0; k < RPL; ++k)
-                full |= (unsigned long long)__ballot_sync(FULL, (lane + 32 * k < H) && row[k] == p.fullmask) << (32 * k);
-            const int k_cleared = __popcll(full);
-            if (k_cleared) {
-                unsigned long long f = full;
-                while (f) {  // top-most full row first; rows below it keep their index
-                    const int fr = __ffsll((long long)f) - 1;
-                    f &= f - 1;
-                    remove_row<RPL>(row, fr, lane);
-                }
-                if (lane == 4) sw += k_cleared;  // lines_cleared (ref:213)
-            }
-            // line-clear reward / score (ref:266-275)
-            int dscore;
-            if (p.adv_clears) {
-                const int kk = k_cleared > 4 ? 4 : k_cleared;
-                dscore = kk == 0 ? 0 : kk == 1 ? 40 : kk == 2 ? 100 : kk == 3 ? 300 : 1200;
-                reward += (dscore * 5) / 2;  // 2.5 * {0,40,100,300,1200} is integral
-            } else if (p.high_scoring) {
-                dscore = k_cleared;
-                reward += 1000 * k_cleared;
-            } else {
-                dscore = k_cleared;
-                reward += 100 * k_cleared;
-            }
-            if (lane == 3) sw += dscore;
-            const int old_holes = get(sw, 5);
-            const int holes = count_holes<RPL>(row, H, p.fullmask, lane);  // ref:278,284
-            put(sw, lane, 5, holes);
-            const bool top = (__ballot_sync(FULL, row[0] != 0u) & 1u) != 0u;  // np.any(board[:,0]) ref:277
-            if (top) {
-                if (lane == 7) sw += 1;  // n_deaths (ref:279)
-                done = 1;
-                reward = -100;  // ref:281 overrides everything
-            } else {
-                if (p.pen_height) {  // ref:286-287
-                    reward -= nonempty_rows<RPL>(row);
-                } else if (p.pen_height_inc) {  // ref:288-292
-                    const int nh = nonempty_rows<RPL>(row);
-                    const int ph = get(sw, 6);
-                    if (nh > ph) reward -= 10 * (nh - ph);
-                    put(sw, lane, 6, nh);
-                }
-                if (p.pen_holes) reward -= 5 * holes;  // ref:294-297
-                else if (p.pen_holes_inc) reward -= 5 * (holes - old_holes);
-                pc.id = spawn_piece(sw, lane, p, e, errbits);  // _new_piece ref:299
-                pc.rot = 0; pc.x = W / 2; pc.y = 0;
-                pr = piece_rows(pc.id, 0, pc.x, W, p.fullmask);
-            }
-        }
+        ld += 1;  // ref:175,260: (x + 1) % (max(lock_delay, 0) + 1)
+        if (ld >= p.lock_mod) ld %= p.lock_mod;
+        if (ld == 0) engine_lock<RPL, RowT>(row, sw, pc, pr, lane, p, e, reward, done, errbits, walls);
     }
     put(sw, lane, 1, ld);
     // ---- compose the returned state (ref:301-303): draw, copy, erase ----
-    uint32_t pm[RPL];
-    piece_on_rows<RPL>(pm, pr, pc.y, lane);
+    RowT pm[RPL];
+    piece_on_rows<RPL, RowT>(pm, pr, pc.y, lane);
 #pragma unroll
     for (int k = 0; k < RPL; ++k) {
         disp[k] = row[k] | pm[k];
-        row[k] &= ~pm[k];  // _set_piece(False) also wipes a just-locked piece after game over (ref:303)
+        row[k] = (row[k] & ~pm[k]) | walls;  // _set_piece(False) also wipes a just-locked piece after game over (ref:303)
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // Observation writers
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float bitf(uint32_t r, int x) { return ((r >> x) & 1u) ? 1.0f : 0.0f; }
-
 // ram (ref:421-424 + float32 cast ref:400): out[x][y] = cell (x,y); rows come from the warp's smem row.
 __device__ __forceinline__ void write_ram(const uint32_t *srow, float *out, const Params &p, int lane)
 {
     const int H = p.H, W = p.W;
     if ((H & 3) == 0) {
-        const int nq = (W * H) >> 2;
+        const int nq = (W * H) >> 2, hq = H >> 2;
         float4 *o4 = reinterpret_cast<float4 *>(out);
         for (int q = lane; q < nq; q += 32) {
             const int x = (int)(((uint32_t)q * p.inv_hq20) >> 20);
-            const int y0 = (q - x * (H >> 2)) << 2;
+            const int y0 = (q - x * hq) << 2;
+            const uint32_t bit = 1u << x;
             const uint4 r = *reinterpret_cast<const uint4 *>(srow + y0);
-            o4[q] = make_float4(bitf(r.x, x), bitf(r.y, x), bitf(r.z, x), bitf(r.w, x));
+            o4[q] = make_float4((r.x & bit) ? 1.0f : 0.0f, (r.y & bit) ? 1.0f : 0.0f, (r.z & bit) ? 1.0f : 0.0f,
+                                (r.w & bit) ? 1.0f : 0.0f);
         }
     } else {
         const int nel = W * H;
         for (int i = lane; i < nel; i += 32) {
             const int x = (int)(((uint32_t)i * p.inv_h20) >> 20);
             const int yy = i - x * H;
-            out[i] = bitf(srow[yy], x);
+            out[i] = ((srow[yy] >> x) & 1u) ? 1.0f : 0.0f;
         }
     }
 }
@@ -447,17 +421,19 @@ __device__ __forceinline__ ColSlot make_col_slot(int k, const Params &p)
 }
 
 // ---------------------------------------------------------------------------------------------
-// The step / reset / observe kernel.  OBS: 0 ram, 1 grayscale, 2 rgb.
+// The step / reset / observe kernel.  OBS: 0 ram, 1 grayscale, 2 rgb.  MODE is a template parameter so
+// that the step kernel carries no reset/observe code.
 // ---------------------------------------------------------------------------------------------
-template <int RPL, int OBS>
+template <int RPL, int OBS, int MODE, typename RowT>
 __global__ void __launch_bounds__(kThreads) st_main_kernel(const __grid_constant__ Params p)
 {
-    __shared__ __align__(16) uint32_t s_disp[kWarpsPerCta][64];
-    __shared__ signed char s_rowy[kImage];
+    __shared__ __align__(16) uint32_t s_disp[kWarpsPerCta][32 * RPL];
+    __shared__ signed char s_rowy[OBS == 0 ? 1 : kImage];
     __shared__ unsigned char s_active[kWarpsPerCta];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int H = p.H;
+    const RowT walls = (RowT)0xF | (~(RowT)0 << (p.W + OFF));
     constexpr int CH = OBS == 2 ? 3 : 1;
     constexpr int KPR = kImage * CH / 4;  // float4 slots per image row: 21 / 63
     constexpr int NG = 252 / KPR;         // row groups: 12 / 4
@@ -473,18 +449,16 @@ __global__ void __launch_bounds__(kThreads) st_main_kernel(const __grid_constant
         }
     }
 
-    const long long ngroups = (p.n + kWarpsPerCta - 1) / kWarpsPerCta;
-    for (long long g = blockIdx.x; g < ngroups; g += gridDim.x) {
-        const long long e = g * kWarpsPerCta + warp;
+    const int ngroups = (int)((p.n + kWarpsPerCta - 1) / kWarpsPerCta);
+    for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        const long long e = (long long)g * kWarpsPerCta + warp;
         const bool valid = e < p.n;
-        uint32_t row[RPL], disp[RPL];
+        RowT row[RPL], disp[RPL], row_in[RPL];
         int sw = 0, errbits = 0;
         Piece pc = {7, 0, 0, 0};
         unsigned char *rec = p.state + (valid ? e : 0) * (long long)p.stride;
         bool selected = valid;
-        if (valid) {
-            if (p.mode == MODE_RESET && p.mask && p.mask[e] == 0) selected = false;
-        }
+        if (MODE == MODE_RESET && valid && p.mask && p.mask[e] == 0) selected = false;
         if (selected) {
             if (lane < kStateWords) sw = reinterpret_cast<const int *>(rec)[lane];
 #pragma unroll
@@ -493,24 +467,23 @@ __global__ void __launch_bounds__(kThreads) st_main_kernel(const __grid_constant
                 uint32_t v = 0;
                 if (Y < H) v = p.row_bytes == 2 ? (uint32_t)reinterpret_cast<const uint16_t *>(rec + 4 * kStateWords)[Y]
                                                 : reinterpret_cast<const uint32_t *>(rec + 4 * kStateWords)[Y];
-                row[k] = v;
+                row[k] = ((RowT)v << OFF) | walls;
             }
             pc = unpack_piece(get(sw, 0));
         } else {
 #pragma unroll
-            for (int k = 0; k < RPL; ++k) row[k] = 0;
+            for (int k = 0; k < RPL; ++k) row[k] = walls;
         }
-        uint32_t row_in[RPL];
 #pragma unroll
-        for (int k = 0; k < RPL; ++k) row_in[k] = row[k];
+        for (int k = 0; k < RPL; ++k) { row_in[k] = row[k]; disp[k] = row[k]; }
 
-        const int T = p.mode == MODE_STEP ? p.T : 1;
+        const int T = MODE == MODE_STEP ? p.T : 1;
         for (int t = 0; t < T; ++t) {
             if (selected) {
-                int reward = 0, done = 0;
-                if (p.mode == MODE_STEP) {
+                if (MODE == MODE_STEP) {
+                    int reward = 0, done = 0;
                     const int action = p.actions[(long long)t * p.n + e];
-                    engine_step<RPL>(row, disp, sw, pc, action, lane, p, e, reward, done, errbits);
+                    engine_step<RPL, RowT>(row, disp, sw, pc, action, lane, p, e, reward, done, errbits, walls);
                     put(sw, lane, 0, pack_piece(pc));
                     if (p.info && lane < kStateWords)  // get_info (ref:232-241) before any auto-reset
                         p.info[(long long)t * p.info_t_stride + e * kStateWords + lane] = lane == 0 ? pc.id : sw;
@@ -519,35 +492,35 @@ __global__ void __launch_bounds__(kThreads) st_main_kernel(const __grid_constant
                             atomicAdd(p.stats + (lane == 2 ? 1 : lane == 3 ? 3 : 2), (unsigned long long)(long long)sw);
                         if (p.stats && lane == 0) atomicAdd(p.stats, 1ull);
                         if (p.auto_reset) {  // VecEnv: reset obs = empty board, piece not drawn (ref:313-315)
-                            engine_clear<RPL>(row, sw, pc, lane, p, e, errbits);
+                            engine_clear<RPL, RowT>(row, sw, pc, lane, p, e, errbits, walls);
                             put(sw, lane, 0, pack_piece(pc));
 #pragma unroll
-                            for (int k = 0; k < RPL; ++k) disp[k] = 0;
+                            for (int k = 0; k < RPL; ++k) disp[k] = walls;
                         }
                     }
                     if (lane == 0) {
                         p.reward[(long long)t * p.n + e] = (float)reward;
                         p.done[(long long)t * p.n + e] = (unsigned char)done;
                     }
-                } else if (p.mode == MODE_RESET) {
-                    engine_clear<RPL>(row, sw, pc, lane, p, e, errbits);
+                } else if (MODE == MODE_RESET) {
+                    engine_clear<RPL, RowT>(row, sw, pc, lane, p, e, errbits, walls);
                     put(sw, lane, 0, pack_piece(pc));
 #pragma unroll
-                    for (int k = 0; k < RPL; ++k) disp[k] = 0;
+                    for (int k = 0; k < RPL; ++k) disp[k] = walls;
                 } else {  // MODE_OBSERVE: engine.render() (ref:317-321) or the bare board
-                    uint32_t pm[RPL];
+                    RowT pm[RPL];
 #pragma unroll
                     for (int k = 0; k < RPL; ++k) pm[k] = 0;
                     if (p.draw_piece && pc.id < 7) {
-                        const PieceRows pr = piece_rows(pc.id, pc.rot, pc.x, p.W, p.fullmask);
-                        piece_on_rows<RPL>(pm, pr, pc.y, lane);
+                        const PieceRows<RowT> pr = piece_rows<RowT>(pc.id, pc.rot, pc.x);
+                        piece_on_rows<RPL, RowT>(pm, pr, pc.y, lane);
                     }
 #pragma unroll
                     for (int k = 0; k < RPL; ++k) disp[k] = row[k] | pm[k];
                 }
                 if (p.obs) {
 #pragma unroll
-                    for (int k = 0; k < RPL; ++k) s_disp[warp][lane + 32 * k] = disp[k];
+                    for (int k = 0; k < RPL; ++k) s_disp[warp][lane + 32 * k] = (uint32_t)(disp[k] >> OFF) & p.fullmask;
                 }
             }
             float *obs_t = p.obs ? p.obs + (long long)t * p.obs_t_stride : nullptr;
@@ -559,7 +532,7 @@ __global__ void __launch_bounds__(kThreads) st_main_kernel(const __grid_constant
                 if (lane == 0) s_active[warp] = selected && obs_t;
                 __syncthreads();
                 if (threadIdx.x < KPR * NG) {
-                    float4 *base = reinterpret_cast<float4 *>(obs_t + g * kWarpsPerCta * (long long)p.obs_elems) + slot_k;
+                    float4 *base = reinterpret_cast<float4 *>(obs_t + (long long)g * kWarpsPerCta * p.obs_elems) + slot_k;
                     for (int rho = slot_g; rho < kImage; rho += NG) {
                         const int code = s_rowy[rho];
 #pragma unroll
@@ -580,7 +553,7 @@ __global__ void __launch_bounds__(kThreads) st_main_kernel(const __grid_constant
             }
         }
 
-        if (selected && p.mode != MODE_OBSERVE) {
+        if (selected && MODE != MODE_OBSERVE) {
             if (lane < kStateWords) reinterpret_cast<int *>(rec)[lane] = sw;
             bool dirty = false;
 #pragma unroll
@@ -589,9 +562,10 @@ __global__ void __launch_bounds__(kThreads) st_main_kernel(const __grid_constant
 #pragma unroll
                 for (int k = 0; k < RPL; ++k) {
                     const int Y = lane + 32 * k;
+                    const uint32_t v = (uint32_t)(row[k] >> OFF) & p.fullmask;
                     if (Y < H) {
-                        if (p.row_bytes == 2) reinterpret_cast<uint16_t *>(rec + 4 * kStateWords)[Y] = (uint16_t)row[k];
-                        else reinterpret_cast<uint32_t *>(rec + 4 * kStateWords)[Y] = row[k];
+                        if (p.row_bytes == 2) reinterpret_cast<uint16_t *>(rec + 4 * kStateWords)[Y] = (uint16_t)v;
+                        else reinterpret_cast<uint32_t *>(rec + 4 * kStateWords)[Y] = v;
                     }
                 }
             }
@@ -668,28 +642,44 @@ static unsigned long long g_launches = 0;
 unsigned long long launch_count() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 static inline void count_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
 
-template <int RPL, int OBS>
+template <int RPL, int OBS, int MODE, typename RowT>
 static cudaError_t launch_t(const Params &p, cudaStream_t stream)
 {
     const long long ngroups = (p.n + kWarpsPerCta - 1) / kWarpsPerCta;
     if (ngroups == 0) return cudaSuccess;
-    const long long maxgrid = 1ll << 30;
-    const unsigned grid = (unsigned)(ngroups < maxgrid ? ngroups : maxgrid);
-    st_main_kernel<RPL, OBS><<<grid, kThreads, 0, stream>>>(p);
+    st_main_kernel<RPL, OBS, MODE, RowT><<<(unsigned)ngroups, kThreads, 0, stream>>>(p);
     count_launch();
     return cudaGetLastError();
 }
 
+template <int RPL, int OBS, typename RowT>
+static cudaError_t launch_mode(const Params &p, cudaStream_t stream)
+{
+    switch (p.mode) {
+    case MODE_STEP: return launch_t<RPL, OBS, MODE_STEP, RowT>(p, stream);
+    case MODE_RESET: return launch_t<RPL, OBS, MODE_RESET, RowT>(p, stream);
+    case MODE_OBSERVE: return launch_t<RPL, OBS, MODE_OBSERVE, RowT>(p, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <int OBS>
+static cudaError_t launch_obs(const Params &p, cudaStream_t stream)
+{
+    const bool two = p.H > 31, wide = p.W + OFF + 3 > 31;  // piece bits reach column W + 2
+    if (!two && !wide) return launch_mode<1, OBS, uint32_t>(p, stream);
+    if (two && !wide) return launch_mode<2, OBS, uint32_t>(p, stream);
+    if (!two && wide) return launch_mode<1, OBS, unsigned long long>(p, stream);
+    return launch_mode<2, OBS, unsigned long long>(p, stream);
+}
+
 cudaError_t launch_main(const Params &p, int obs_type, cudaStream_t stream)
 {
-    const int rpl = p.H > 31 ? 2 : 1;
-    switch (rpl * 10 + obs_type) {
-    case 10: return launch_t<1, 0>(p, stream);
-    case 11: return launch_t<1, 1>(p, stream);
-    case 12: return launch_t<1, 2>(p, stream);
-    case 20: return launch_t<2, 0>(p, stream);
-    case 21: return launch_t<2, 1>(p, stream);
-    case 22: return launch_t<2, 2>(p, stream);
+    if (p.n >= (1ll << 31) - 8) return cudaErrorInvalidValue;
+    switch (obs_type) {
+    case 0: return launch_obs<0>(p, stream);
+    case 1: return launch_obs<1>(p, stream);
+    case 2: return launch_obs<2>(p, stream);
     }
     return cudaErrorInvalidValue;
 }

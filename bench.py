@@ -150,6 +150,7 @@ def time_workload(name, steps, warmup, rank, world, dist, burn_in=200):
         envs.append(env)
     actions = torch.randint(0, 7, (warmup + steps, n), dtype=torch.uint8, device=dev, generator=g)
     stream = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize(dev)  # set-up ran on the default stream; the side stream does not wait for it
     graphs = []
     with torch.cuda.stream(stream):
         for t in range(warmup):

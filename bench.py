@@ -208,7 +208,7 @@ def time_workload(name, steps, warmup, rank, world, dist, burn_in=200):
     return res
 
 
-def time_e2e(name, steps, warmup, rank, world, dist):
+def time_e2e(name, steps, warmup, rank, world, dist, zero_copy=None):
     """Same metric through the host-buffer C ABI: pinned host actions in, obs/reward/done/info out, every step."""
     import ctypes as C
 
@@ -227,6 +227,8 @@ def time_e2e(name, steps, warmup, rank, world, dist):
     h = L.st_host_create(C.byref(cfg), n)
     if not h:
         raise RuntimeError("st_host_create: " + L.st_last_error().decode())
+    if zero_copy is not None:
+        native.check(L.st_host_set_zero_copy(h, int(zero_copy)), "st_host_set_zero_copy")
     elems = int(L.st_obs_elems(C.byref(cfg)))
     obs = torch.empty((n, elems), dtype=torch.float32).pin_memory()
     reward = torch.empty(n, dtype=torch.float32).pin_memory()

@@ -224,6 +224,10 @@ struct StHostEnv {
     unsigned long long *stats;
     uint8_t *boards;
     int32_t *scalars;
+    int zero_copy;  // ST_ZC_* mask
+    // cache of the last host pointers seen and their device-side aliases (NULL = not page-locked)
+    const void *zc_host[5];
+    void *zc_dev[5];
 };
 
 #define HCHECK(call, where)                                  \
@@ -243,6 +247,28 @@ static StAux host_aux(const StHostEnv *h)
     return a;
 }
 
+// Device-side alias of a page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory) host pointer, or
+// NULL for pageable memory.  One driver query per distinct pointer; steady-state calls hit the cache.
+static void *mapped_alias(StHostEnv *h, int slot, const void *host)
+{
+    if (!host) return nullptr;
+    if (h->zc_host[slot] == host) return h->zc_dev[slot];
+    cudaPointerAttributes a;
+    void *dev = nullptr;
+    if (cudaPointerGetAttributes(&a, host) == cudaSuccess && a.type == cudaMemoryTypeHost) dev = a.devicePointer;
+    else cudaGetLastError();
+    h->zc_host[slot] = host;
+    h->zc_dev[slot] = dev;
+    return dev;
+}
+
+int st_host_set_zero_copy(StHostEnv *h, int32_t mask)
+{
+    if (!h) return fail(ST_E_INVALID, "NULL handle%s");
+    h->zero_copy = mask;
+    return 0;
+}
+
 StHostEnv *st_host_create(const StConfig *cfg, int64_t n)
 {
     if (!config_ok(cfg) || n < 1) {
@@ -256,6 +282,9 @@ StHostEnv *st_host_create(const StConfig *cfg, int64_t n)
     h->cfg = *cfg;
     h->n = n;
     h->obs_elems = st_obs_elems(cfg);
+    // small batches: the kernel writes straight into page-locked caller buffers (saves four copy launches);
+    // large ones: the copy engine moves the observation block at link rate
+    h->zero_copy = (n * (h->obs_elems * 4 + 65) <= (8ll << 20)) ? (ST_ZC_ACTIONS | ST_ZC_SMALL | ST_ZC_OBS) : 0;
     bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaMalloc(&h->state, (size_t)(st_state_stride(cfg) * n)) == cudaSuccess;
     ok = ok && cudaMalloc((void **)&h->actions, (size_t)n) == cudaSuccess;
@@ -325,19 +354,31 @@ int st_host_step(StHostEnv *h, const uint8_t *actions, float *obs, float *reward
 {
     if (!h || !actions) return fail(ST_E_INVALID, "NULL handle/actions%s");
     if (int rc = use_device(&h->cfg)) return rc;
-    HCHECK(cudaMemcpyAsync(h->actions, actions, (size_t)h->n, cudaMemcpyHostToDevice, h->stream), "H2D actions");
+    // Page-locked caller buffers can be read / written by the kernel itself over PCIe (no staging copy, no
+    // extra copy launches); pageable ones go through the handle's device buffers and cudaMemcpyAsync.
+    const int zc = h->zero_copy;
+    const uint8_t *d_act = (zc & ST_ZC_ACTIONS) ? (const uint8_t *)mapped_alias(h, 0, actions) : nullptr;
+    float *d_obs = (zc & ST_ZC_OBS) ? (float *)mapped_alias(h, 1, obs) : nullptr;
+    float *d_rew = (zc & ST_ZC_SMALL) ? (float *)mapped_alias(h, 2, reward) : nullptr;
+    uint8_t *d_done = (zc & ST_ZC_SMALL) ? (uint8_t *)mapped_alias(h, 3, done) : nullptr;
+    int32_t *d_info = (zc & ST_ZC_SMALL) ? (int32_t *)mapped_alias(h, 4, info) : nullptr;
+    if (!d_act) {
+        HCHECK(cudaMemcpyAsync(h->actions, actions, (size_t)h->n, cudaMemcpyHostToDevice, h->stream), "H2D actions");
+        d_act = h->actions;
+    }
     StAux aux = host_aux(h);
-    if (int rc = st_step(&h->cfg, h->state, h->actions, h->obs, h->reward, h->done, info ? h->info : nullptr, &aux,
-                         h->n, h->stream))
+    if (int rc = st_step(&h->cfg, h->state, d_act, d_obs ? d_obs : h->obs, d_rew ? d_rew : h->reward,
+                         d_done ? d_done : h->done, info ? (d_info ? d_info : h->info) : nullptr, &aux, h->n,
+                         h->stream))
         return rc;
-    if (obs)
+    if (obs && !d_obs)
         HCHECK(cudaMemcpyAsync(obs, h->obs, (size_t)(h->obs_elems * h->n) * sizeof(float), cudaMemcpyDeviceToHost,
                                h->stream), "D2H obs");
-    if (reward)
+    if (reward && !d_rew)
         HCHECK(cudaMemcpyAsync(reward, h->reward, (size_t)h->n * sizeof(float), cudaMemcpyDeviceToHost, h->stream),
                "D2H reward");
-    if (done) HCHECK(cudaMemcpyAsync(done, h->done, (size_t)h->n, cudaMemcpyDeviceToHost, h->stream), "D2H done");
-    if (info)
+    if (done && !d_done) HCHECK(cudaMemcpyAsync(done, h->done, (size_t)h->n, cudaMemcpyDeviceToHost, h->stream), "D2H done");
+    if (info && !d_info)
         HCHECK(cudaMemcpyAsync(info, h->info, (size_t)h->n * ST_INFO_WORDS * sizeof(int32_t), cudaMemcpyDeviceToHost,
                                h->stream), "D2H info");
     HCHECK(cudaStreamSynchronize(h->stream), "st_host_step");

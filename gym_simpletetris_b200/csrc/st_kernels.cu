@@ -129,7 +129,7 @@ __device__ __forceinline__ uint32_t philox_draw(uint32_t k0, uint32_t k1, unsign
 
 // _new_piece / _choose_shape (ref:183-200).  `sw` is this lane's word of the env record (lanes 8..14
 // hold shape_counts).  Returns the piece id; bumps its count.
-__device__ __forceinline__ int spawn_piece(int &sw, int lane, const Params &p, long long e, int &errbits)
+__device__ __forceinline__ int spawn_piece(int &sw, int lane, const Params &p, int e, int &errbits)
 {
     int c[7];
     int total = 0, mx = 0;
@@ -143,7 +143,7 @@ __device__ __forceinline__ int spawn_piece(int &sw, int lane, const Params &p, l
     if (p.queue) {
         int k = total;
         if (k >= p.queue_len) { errbits |= 1; k %= p.queue_len; }
-        id = p.queue[e * p.queue_len + k] % 7;
+        id = p.queue[(size_t)e * (unsigned)p.queue_len + k] % 7;
     } else {
         const int S = 35 + 7 * mx - total;  // sum of m_i = 5 + max - c_i (ref:186)
         const uint32_t u = philox_draw(p.seed_lo, p.seed_hi, (unsigned long long)(p.env_id_base + e), (uint32_t)total);
@@ -229,7 +229,7 @@ __device__ __forceinline__ int get(int sw, int idx) { return __shfl_sync(FULL, s
 // deaths and shape_counts persist.
 template <int RPL, typename RowT>
 __device__ __forceinline__ void engine_clear(RowT (&row)[RPL], int &sw, Piece &pc, int lane, const Params &p,
-                                             long long e, int &errbits, RowT walls)
+                                             int e, int &errbits, RowT walls)
 {
     if (lane >= 2 && lane <= 6) sw = 0;  // time, score, lines_cleared, holes, piece_height
     pc.id = spawn_piece(sw, lane, p, e, errbits);
@@ -241,7 +241,7 @@ __device__ __forceinline__ void engine_clear(RowT (&row)[RPL], int &sw, Piece &p
 // The lock branch of TetrisEngine.step (ref:262-299), out of line: taken on ~1/5 of the steps.
 template <int RPL, typename RowT>
 __device__ __forceinline__ void engine_lock(RowT (&row)[RPL], int &sw, Piece &pc, PieceRows<RowT> &pr, int lane,
-                                         const Params &p, long long e, int &reward, int &done, int &errbits, RowT walls)
+                                         const Params &p, int e, int &reward, int &done, int &errbits, RowT walls)
 {
     const int H = p.H;
     RowT pm[RPL];
@@ -307,7 +307,7 @@ __device__ __forceinline__ void engine_lock(RowT (&row)[RPL], int &sw, Piece &pc
 // TetrisEngine.step (ref:243-304).  Outputs reward/done and the display rows (board | piece, ref:301-302).
 template <int RPL, typename RowT>
 __device__ __forceinline__ void engine_step(RowT (&row)[RPL], RowT (&disp)[RPL], int &sw, Piece &pc, int action,
-                                            int lane, const Params &p, long long e, int &reward, int &done,
+                                            int lane, const Params &p, int e, int &reward, int &done,
                                             int &errbits, RowT walls)
 {
     using M = typename CMask<RPL>::type;
@@ -381,9 +381,9 @@ __device__ __forceinline__ void write_ram(const uint32_t *srow, float *out, cons
         float4 *o4 = reinterpret_cast<float4 *>(out);
         for (int q = lane; q < nq; q += 32) {
             const int x = (int)(((uint32_t)q * p.inv_hq20) >> 20);
-            const int y0 = (q - x * hq) << 2;
+            const int yq = q - x * hq;
             const uint32_t bit = 1u << x;
-            const uint4 r = *reinterpret_cast<const uint4 *>(srow + y0);
+            const uint4 r = reinterpret_cast<const uint4 *>(srow)[yq];
             o4[q] = make_float4((r.x & bit) ? 1.0f : 0.0f, (r.y & bit) ? 1.0f : 0.0f, (r.z & bit) ? 1.0f : 0.0f,
                                 (r.w & bit) ? 1.0f : 0.0f);
         }
@@ -433,6 +433,10 @@ __global__ void __launch_bounds__(kThreads) st_main_kernel(const __grid_constant
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int H = p.H;
+    const int n = (int)p.n;
+    const int e = blockIdx.x * kWarpsPerCta + warp;  // this warp's env (launch_main keeps n below 2^31)
+    const bool valid = e < n;
+    if (OBS == 0 && !valid) return;  // ram warps never meet at a CTA barrier
     const RowT walls = (RowT)0xF | (~(RowT)0 << (p.W + OFF));
     constexpr int CH = OBS == 2 ? 3 : 1;
     constexpr int KPR = kImage * CH / 4;  // float4 slots per image row: 21 / 63
@@ -449,129 +453,136 @@ __global__ void __launch_bounds__(kThreads) st_main_kernel(const __grid_constant
         }
     }
 
-    const int ngroups = (int)((p.n + kWarpsPerCta - 1) / kWarpsPerCta);
-    for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
-        const long long e = (long long)g * kWarpsPerCta + warp;
-        const bool valid = e < p.n;
-        RowT row[RPL], disp[RPL], row_in[RPL];
-        int sw = 0, errbits = 0;
-        Piece pc = {7, 0, 0, 0};
-        unsigned char *rec = p.state + (valid ? e : 0) * (long long)p.stride;
-        bool selected = valid;
-        if (MODE == MODE_RESET && valid && p.mask && p.mask[e] == 0) selected = false;
+    bool selected = valid;
+    if (MODE == MODE_RESET && valid && p.mask && p.mask[e] == 0) selected = false;
+    unsigned char *rec = p.state + (size_t)(valid ? e : 0) * (unsigned)p.stride;
+    int *rec_w = reinterpret_cast<int *>(rec);
+    RowT row[RPL], disp[RPL], row_in[RPL];
+    int sw = 0, errbits = 0;
+    Piece pc = {7, 0, 0, 0};
+    if (selected) {
+        if (lane < kStateWords) sw = rec_w[lane];
+#pragma unroll
+        for (int k = 0; k < RPL; ++k) {
+            const int Y = lane + 32 * k;
+            uint32_t v = 0;
+            if (Y < H) v = p.row_bytes == 2 ? (uint32_t)reinterpret_cast<const uint16_t *>(rec_w + kStateWords)[Y]
+                                            : reinterpret_cast<const uint32_t *>(rec_w + kStateWords)[Y];
+            row[k] = ((RowT)v << OFF) | walls;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < RPL; ++k) row[k] = walls;
+    }
+    // running output pointers (advance per step in st_step_many)
+    const uint8_t *act_p = MODE == MODE_STEP ? p.actions + e : nullptr;
+    float *rew_p = MODE == MODE_STEP ? p.reward + e : nullptr;
+    uint8_t *done_p = MODE == MODE_STEP ? p.done + e : nullptr;
+    int32_t *info_p = (MODE == MODE_STEP && p.info) ? p.info + (size_t)e * kStateWords + lane : nullptr;
+    float *obs_p = p.obs ? p.obs + (size_t)(OBS == 0 ? e : (int)blockIdx.x * kWarpsPerCta) * (unsigned)p.obs_elems : nullptr;
+    int action = 6;
+    if (MODE == MODE_STEP && selected) action = *act_p;  // issued together with the state loads
+    if (selected) pc = unpack_piece(get(sw, 0));
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) { row_in[k] = row[k]; disp[k] = row[k]; }
+
+    const int T = MODE == MODE_STEP ? p.T : 1;
+    for (int t = 0; t < T; ++t) {
         if (selected) {
-            if (lane < kStateWords) sw = reinterpret_cast<const int *>(rec)[lane];
+            if (MODE == MODE_STEP) {
+                int reward = 0, done = 0;
+                engine_step<RPL, RowT>(row, disp, sw, pc, action, lane, p, e, reward, done, errbits, walls);
+                put(sw, lane, 0, pack_piece(pc));
+                if (info_p && lane < kStateWords) *info_p = lane == 0 ? pc.id : sw;  // get_info (ref:232-241), pre-reset
+                if (done) {
+                    if (p.stats && lane >= 2 && lane <= 4)  // sum(time), sum(score), sum(lines) at done
+                        atomicAdd(p.stats + (lane == 2 ? 1 : lane == 3 ? 3 : 2), (unsigned long long)(long long)sw);
+                    if (p.stats && lane == 0) atomicAdd(p.stats, 1ull);
+                    if (p.auto_reset) {  // VecEnv: reset obs = empty board, piece not drawn (ref:313-315)
+                        engine_clear<RPL, RowT>(row, sw, pc, lane, p, e, errbits, walls);
+                        put(sw, lane, 0, pack_piece(pc));
+#pragma unroll
+                        for (int k = 0; k < RPL; ++k) disp[k] = walls;
+                    }
+                }
+                if (lane == 0) {
+                    *rew_p = (float)reward;
+                    *done_p = (unsigned char)done;
+                }
+                if (t + 1 < T) {  // next step of st_step_many
+                    act_p += n; rew_p += n; done_p += n;
+                    if (info_p) info_p += p.info_t_stride;
+                    action = *act_p;
+                }
+            } else if (MODE == MODE_RESET) {
+                engine_clear<RPL, RowT>(row, sw, pc, lane, p, e, errbits, walls);
+                put(sw, lane, 0, pack_piece(pc));
+#pragma unroll
+                for (int k = 0; k < RPL; ++k) disp[k] = walls;
+            } else {  // MODE_OBSERVE: engine.render() (ref:317-321) or the bare board
+                RowT pm[RPL];
+#pragma unroll
+                for (int k = 0; k < RPL; ++k) pm[k] = 0;
+                if (p.draw_piece && pc.id < 7) {
+                    const PieceRows<RowT> pr = piece_rows<RowT>(pc.id, pc.rot, pc.x);
+                    piece_on_rows<RPL, RowT>(pm, pr, pc.y, lane);
+                }
+#pragma unroll
+                for (int k = 0; k < RPL; ++k) disp[k] = row[k] | pm[k];
+            }
+            if (obs_p) {
+#pragma unroll
+                for (int k = 0; k < RPL; ++k) s_disp[warp][lane + 32 * k] = (uint32_t)(disp[k] >> OFF) & p.fullmask;
+            }
+        }
+        if (OBS == 0) {
+            __syncwarp();
+            if (obs_p) write_ram(s_disp[warp], obs_p, p, lane);
+            __syncwarp();
+        } else {
+            if (lane == 0) s_active[warp] = selected && obs_p;
+            __syncthreads();
+            if (threadIdx.x < KPR * NG) {
+                float4 *base = reinterpret_cast<float4 *>(obs_p) + slot_k;
+                for (int rho = slot_g; rho < kImage; rho += NG) {
+                    const int code = s_rowy[rho];
+#pragma unroll
+                    for (int w = 0; w < kWarpsPerCta; ++w) {
+                        if (!s_active[w]) continue;
+                        const uint32_t b = code >= 0 ? s_disp[w][code] : 0u;
+                        float4 v;
+                        v.x = (b & cs.mk[0]) ? cs.hi[0] : cs.lo[0];
+                        v.y = (b & cs.mk[1]) ? cs.hi[1] : cs.lo[1];
+                        v.z = (b & cs.mk[2]) ? cs.hi[2] : cs.lo[2];
+                        v.w = (b & cs.mk[3]) ? cs.hi[3] : cs.lo[3];
+                        if (code == -2) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        base[(size_t)w * (unsigned)(p.obs_elems >> 2) + rho * KPR] = v;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (obs_p) obs_p += p.obs_t_stride;
+    }
+
+    if (selected && MODE != MODE_OBSERVE) {
+        if (lane < kStateWords) rec_w[lane] = sw;
+        bool dirty = false;
+#pragma unroll
+        for (int k = 0; k < RPL; ++k) dirty |= row[k] != row_in[k];
+        if (__any_sync(FULL, dirty)) {
 #pragma unroll
             for (int k = 0; k < RPL; ++k) {
                 const int Y = lane + 32 * k;
-                uint32_t v = 0;
-                if (Y < H) v = p.row_bytes == 2 ? (uint32_t)reinterpret_cast<const uint16_t *>(rec + 4 * kStateWords)[Y]
-                                                : reinterpret_cast<const uint32_t *>(rec + 4 * kStateWords)[Y];
-                row[k] = ((RowT)v << OFF) | walls;
-            }
-            pc = unpack_piece(get(sw, 0));
-        } else {
-#pragma unroll
-            for (int k = 0; k < RPL; ++k) row[k] = walls;
-        }
-#pragma unroll
-        for (int k = 0; k < RPL; ++k) { row_in[k] = row[k]; disp[k] = row[k]; }
-
-        const int T = MODE == MODE_STEP ? p.T : 1;
-        for (int t = 0; t < T; ++t) {
-            if (selected) {
-                if (MODE == MODE_STEP) {
-                    int reward = 0, done = 0;
-                    const int action = p.actions[(long long)t * p.n + e];
-                    engine_step<RPL, RowT>(row, disp, sw, pc, action, lane, p, e, reward, done, errbits, walls);
-                    put(sw, lane, 0, pack_piece(pc));
-                    if (p.info && lane < kStateWords)  // get_info (ref:232-241) before any auto-reset
-                        p.info[(long long)t * p.info_t_stride + e * kStateWords + lane] = lane == 0 ? pc.id : sw;
-                    if (done) {
-                        if (p.stats && lane >= 2 && lane <= 4)  // sum(time), sum(score), sum(lines) at done
-                            atomicAdd(p.stats + (lane == 2 ? 1 : lane == 3 ? 3 : 2), (unsigned long long)(long long)sw);
-                        if (p.stats && lane == 0) atomicAdd(p.stats, 1ull);
-                        if (p.auto_reset) {  // VecEnv: reset obs = empty board, piece not drawn (ref:313-315)
-                            engine_clear<RPL, RowT>(row, sw, pc, lane, p, e, errbits, walls);
-                            put(sw, lane, 0, pack_piece(pc));
-#pragma unroll
-                            for (int k = 0; k < RPL; ++k) disp[k] = walls;
-                        }
-                    }
-                    if (lane == 0) {
-                        p.reward[(long long)t * p.n + e] = (float)reward;
-                        p.done[(long long)t * p.n + e] = (unsigned char)done;
-                    }
-                } else if (MODE == MODE_RESET) {
-                    engine_clear<RPL, RowT>(row, sw, pc, lane, p, e, errbits, walls);
-                    put(sw, lane, 0, pack_piece(pc));
-#pragma unroll
-                    for (int k = 0; k < RPL; ++k) disp[k] = walls;
-                } else {  // MODE_OBSERVE: engine.render() (ref:317-321) or the bare board
-                    RowT pm[RPL];
-#pragma unroll
-                    for (int k = 0; k < RPL; ++k) pm[k] = 0;
-                    if (p.draw_piece && pc.id < 7) {
-                        const PieceRows<RowT> pr = piece_rows<RowT>(pc.id, pc.rot, pc.x);
-                        piece_on_rows<RPL, RowT>(pm, pr, pc.y, lane);
-                    }
-#pragma unroll
-                    for (int k = 0; k < RPL; ++k) disp[k] = row[k] | pm[k];
-                }
-                if (p.obs) {
-#pragma unroll
-                    for (int k = 0; k < RPL; ++k) s_disp[warp][lane + 32 * k] = (uint32_t)(disp[k] >> OFF) & p.fullmask;
-                }
-            }
-            float *obs_t = p.obs ? p.obs + (long long)t * p.obs_t_stride : nullptr;
-            if (OBS == 0) {
-                __syncwarp();
-                if (selected && obs_t) write_ram(s_disp[warp], obs_t + e * (long long)p.obs_elems, p, lane);
-                __syncwarp();
-            } else {
-                if (lane == 0) s_active[warp] = selected && obs_t;
-                __syncthreads();
-                if (threadIdx.x < KPR * NG) {
-                    float4 *base = reinterpret_cast<float4 *>(obs_t + (long long)g * kWarpsPerCta * p.obs_elems) + slot_k;
-                    for (int rho = slot_g; rho < kImage; rho += NG) {
-                        const int code = s_rowy[rho];
-#pragma unroll
-                        for (int w = 0; w < kWarpsPerCta; ++w) {
-                            if (!s_active[w]) continue;
-                            const uint32_t b = code >= 0 ? s_disp[w][code] : 0u;
-                            float4 v;
-                            v.x = (b & cs.mk[0]) ? cs.hi[0] : cs.lo[0];
-                            v.y = (b & cs.mk[1]) ? cs.hi[1] : cs.lo[1];
-                            v.z = (b & cs.mk[2]) ? cs.hi[2] : cs.lo[2];
-                            v.w = (b & cs.mk[3]) ? cs.hi[3] : cs.lo[3];
-                            if (code == -2) v = make_float4(0.f, 0.f, 0.f, 0.f);
-                            base[(long long)w * (p.obs_elems >> 2) + rho * KPR] = v;
-                        }
-                    }
-                }
-                __syncthreads();
-            }
-        }
-
-        if (selected && MODE != MODE_OBSERVE) {
-            if (lane < kStateWords) reinterpret_cast<int *>(rec)[lane] = sw;
-            bool dirty = false;
-#pragma unroll
-            for (int k = 0; k < RPL; ++k) dirty |= row[k] != row_in[k];
-            if (__any_sync(FULL, dirty)) {
-#pragma unroll
-                for (int k = 0; k < RPL; ++k) {
-                    const int Y = lane + 32 * k;
-                    const uint32_t v = (uint32_t)(row[k] >> OFF) & p.fullmask;
-                    if (Y < H) {
-                        if (p.row_bytes == 2) reinterpret_cast<uint16_t *>(rec + 4 * kStateWords)[Y] = (uint16_t)v;
-                        else reinterpret_cast<uint32_t *>(rec + 4 * kStateWords)[Y] = v;
-                    }
+                const uint32_t v = (uint32_t)(row[k] >> OFF) & p.fullmask;
+                if (Y < H) {
+                    if (p.row_bytes == 2) reinterpret_cast<uint16_t *>(rec_w + kStateWords)[Y] = (uint16_t)v;
+                    else reinterpret_cast<uint32_t *>(rec_w + kStateWords)[Y] = v;
                 }
             }
         }
-        if (errbits && p.err && lane == 0) atomicOr(p.err, errbits);
     }
+    if (errbits && p.err && lane == 0) atomicOr(p.err, errbits);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -51,6 +51,7 @@ SYMBOLS = {
     "st_host_reset": (C.c_int, [_P, _P, _P]),
     "st_host_step": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "st_host_observe": (C.c_int, [_P, _I32, _P]),
+    "st_host_set_zero_copy": (C.c_int, [_P, _I32]),
     "st_host_get_state": (C.c_int, [_P, _P, _P]),
     "st_host_set_state": (C.c_int, [_P, _P, _P]),
     "st_host_poll": (C.c_int, [_P, _P, _P]),

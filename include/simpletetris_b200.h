@@ -149,6 +149,14 @@ ST_API int st_host_set_piece_queue(StHostEnv *h, const uint8_t *queue, int32_t q
 ST_API int st_host_reset(StHostEnv *h, const uint8_t *mask, float *obs);
 ST_API int st_host_step(StHostEnv *h, const uint8_t *actions, float *obs, float *reward, uint8_t *done, int32_t *info);
 ST_API int st_host_observe(StHostEnv *h, int32_t draw_piece, float *obs);
+/* When a host buffer passed to st_host_step is page-locked (cudaHostAlloc / cudaHostRegister / torch
+ * pin_memory), the kernel can read / write it in place over PCIe instead of staging through device memory.
+ * mask = OR of ST_ZC_*; pageable buffers always take the staging path.  Default: everything in place when one
+ * step's outputs are at most 8 MiB, staging copies (copy engine at link rate) above that. */
+#define ST_ZC_ACTIONS 1 /* kernel reads the actions from host memory */
+#define ST_ZC_SMALL 2   /* reward, done, info written straight to host memory */
+#define ST_ZC_OBS 4     /* observations written straight to host memory */
+ST_API int st_host_set_zero_copy(StHostEnv *h, int32_t mask);
 ST_API int st_host_get_state(StHostEnv *h, uint8_t *boards, int32_t *scalars);
 ST_API int st_host_set_state(StHostEnv *h, const uint8_t *boards, const int32_t *scalars);
 /* Reads and clears the sticky device error flag; stats_out (u64[ST_STATS_WORDS]) may be NULL. */

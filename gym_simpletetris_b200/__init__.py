@@ -8,7 +8,7 @@ When `gym` (or `gymnasium`) is importable the id 'SimpleTetris-v0' is registered
 gym_simpletetris/__init__.py:3-6 does, so `gym.make('SimpleTetris-v0', **kwargs)` works unchanged.
 """
 from . import native  # noqa: F401
-from .envs import TetrisEnv  # noqa: F401
+from .envs import TetrisEnv, TetrisEnvV26  # noqa: F401
 from .sharding import all_reduce_sum, make_sharded_vec_env, shard_bounds  # noqa: F401
 from .vec_env import SHAPE_NAMES, VecEnv  # noqa: F401
 
@@ -25,10 +25,13 @@ def make(env_id=ENV_ID, **kwargs):
 
 
 def _register():
-    for modname in ("gym", "gymnasium"):
+    # gym <= 0.25 speaks the reference's 4-tuple API; gymnasium (and gym >= 0.26) the 5-tuple one
+    for modname, entry in (("gym", ENTRY_POINT), ("gymnasium", ENTRY_POINT + "V26")):
         try:
             mod = __import__(modname + ".envs.registration", fromlist=["register"])
-            mod.register(id=ENV_ID, entry_point=ENTRY_POINT)
+            if modname == "gym" and tuple(int(v) for v in __import__("gym").__version__.split(".")[:2]) >= (0, 26):
+                entry = ENTRY_POINT + "V26"
+            mod.register(id=ENV_ID, entry_point=entry)
         except Exception:  # noqa: BLE001  (not installed, or id already registered)
             pass
 

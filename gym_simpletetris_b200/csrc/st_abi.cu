@@ -180,6 +180,21 @@ int st_observe(const StConfig *cfg, const void *state, int32_t draw_piece, float
     return e == cudaSuccess ? 0 : fail_cuda(e, "st_observe");
 }
 
+int st_render(const StConfig *cfg, const void *state, int32_t draw_piece, int32_t size, uint8_t *out, int64_t n,
+              void *stream)
+{
+    st::Params p;
+    if (int rc = make_params(cfg, nullptr, n, &p)) return rc;
+    if (n && (!state || !out)) return fail(ST_E_INVALID, "state/out is NULL%s");
+    if (size < 4 || size > 4096) return fail(ST_E_INVALID, "render size outside 4..4096%s");
+    if (n >= (1ll << 31)) return fail(ST_E_INVALID, "n too large%s");
+    if (int rc = use_device(cfg)) return rc;
+    p.state = (unsigned char *)const_cast<void *>(state);
+    p.draw_piece = draw_piece;
+    cudaError_t e = st::launch_render(p, size, out, (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail_cuda(e, "st_render");
+}
+
 int st_get_state(const StConfig *cfg, const void *state, uint8_t *boards, int32_t *scalars, int64_t n, void *stream)
 {
     st::Params p;
@@ -260,6 +275,13 @@ static void *mapped_alias(StHostEnv *h, int slot, const void *host)
     h->zc_host[slot] = host;
     h->zc_dev[slot] = dev;
     return dev;
+}
+
+int st_host_set_seed(StHostEnv *h, uint64_t seed)
+{
+    if (!h) return fail(ST_E_INVALID, "NULL handle%s");
+    h->cfg.seed = seed;  // takes effect at the next spawn: the stream is keyed by (seed, env id, piece index)
+    return 0;
 }
 
 int st_host_set_zero_copy(StHostEnv *h, int32_t mask)
@@ -393,6 +415,23 @@ int st_host_observe(StHostEnv *h, int32_t draw_piece, float *obs)
     HCHECK(cudaMemcpyAsync(obs, h->obs, (size_t)(h->obs_elems * h->n) * sizeof(float), cudaMemcpyDeviceToHost,
                            h->stream), "D2H obs");
     HCHECK(cudaStreamSynchronize(h->stream), "st_host_observe");
+    return 0;
+}
+
+int st_host_render(StHostEnv *h, int32_t draw_piece, int32_t size, uint8_t *out)
+{
+    if (!h || !out) return fail(ST_E_INVALID, "NULL handle/out%s");
+    if (int rc = use_device(&h->cfg)) return rc;
+    const size_t nb = (size_t)h->n * size * size * 3;
+    uint8_t *d = nullptr;
+    HCHECK(cudaMalloc((void **)&d, nb), "cudaMalloc(render)");
+    int rc = st_render(&h->cfg, h->state, draw_piece, size, d, h->n, h->stream);
+    cudaError_t e = rc ? cudaSuccess : cudaMemcpyAsync(out, d, nb, cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t e2 = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail_cuda(e, "D2H render");
+    if (e2 != cudaSuccess) return fail_cuda(e2, "st_host_render");
     return 0;
 }
 

@@ -647,6 +647,58 @@ __global__ void st_set_state_kernel(const __grid_constant__ Params p, const uint
 }
 
 // ---------------------------------------------------------------------------------------------
+// K3: TetrisEnv.render('rgb_array') (ref:458-462): engine.render() -> convert_grayscale(obs, size) ->
+// convert_grayscale_rgb, uint8 [n][size][size][3].  One CTA per env; display-only path, kept simple.
+// ---------------------------------------------------------------------------------------------
+struct RenderGeom {
+    int size, pitch, gap, inner_v, inner_h, pad_top, pad_left;
+};
+
+__device__ __forceinline__ uint32_t shade_at(const uint32_t *disp, const RenderGeom &g, int pix)
+{
+    const int r = pix / g.size, c = pix - r * g.size;
+    const int rr = r - g.pad_top, cc = c - g.pad_left;
+    if (rr < 0 || rr >= g.inner_v || cc < 0 || cc >= g.inner_h) return 0u;   // border_shade (ref:77)
+    if ((rr % g.pitch) < g.gap || (cc % g.pitch) < g.gap) return 128u;       // background_shade (ref:78)
+    return ((disp[rr / g.pitch] >> (cc / g.pitch)) & 1u) ? 190u : 128u;      // piece_shade (ref:79)
+}
+
+__global__ void __launch_bounds__(256) st_render_kernel(const __grid_constant__ Params p, const RenderGeom g, uint8_t *out)
+{
+    __shared__ uint32_t disp[64];
+    const long long e = blockIdx.x;
+    const unsigned char *rec = p.state + e * (long long)p.stride;
+    if (threadIdx.x < 64) {
+        const int Y = threadIdx.x;
+        uint32_t v = 0;
+        if (Y < p.H) {
+            v = p.row_bytes == 2 ? (uint32_t)reinterpret_cast<const uint16_t *>(rec + 60)[Y]
+                                 : reinterpret_cast<const uint32_t *>(rec + 60)[Y];
+            const Piece pc = unpack_piece(*reinterpret_cast<const int *>(rec));
+            if (p.draw_piece && pc.id < 7) {  // _set_piece(True) (ref:323-327): in-board cells only
+                const PieceRows<unsigned long long> pr = piece_rows<unsigned long long>(pc.id, pc.rot, pc.x);
+                const int t = Y - pc.y - pr.minj;
+                if (t >= 0 && t < 4) v |= (uint32_t)(pr.m[t] >> OFF) & p.fullmask;
+            }
+        }
+        disp[Y] = v;
+    }
+    __syncthreads();
+    const long long nbytes = (long long)g.size * g.size * 3;
+    uint8_t *o = out + e * nbytes;
+    if ((nbytes & 3) == 0) {
+        uint32_t *o4 = reinterpret_cast<uint32_t *>(o);
+        for (int w = threadIdx.x; w < (int)(nbytes >> 2); w += blockDim.x) {
+            const int b = 4 * w;
+            o4[w] = shade_at(disp, g, b / 3) | (shade_at(disp, g, (b + 1) / 3) << 8) |
+                    (shade_at(disp, g, (b + 2) / 3) << 16) | (shade_at(disp, g, (b + 3) / 3) << 24);
+        }
+    } else {
+        for (int b = threadIdx.x; b < (int)nbytes; b += blockDim.x) o[b] = (uint8_t)shade_at(disp, g, b / 3);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
 static unsigned long long g_launches = 0;
@@ -693,6 +745,25 @@ cudaError_t launch_main(const Params &p, int obs_type, cudaStream_t stream)
     case 2: return launch_obs<2>(p, stream);
     }
     return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_render(const Params &p, int size, uint8_t *out, cudaStream_t stream)
+{
+    if (p.n == 0) return cudaSuccess;
+    RenderGeom g;
+    const int limiting = p.W > p.H ? p.W : p.H;
+    g.size = size;
+    g.gap = size / 100 + 1;                                   // ref:87
+    const int bs = (size - 2 * g.gap) / limiting - g.gap;     // ref:88
+    if (bs < 0) return cudaErrorInvalidValue;                 // the reference raises in np.repeat
+    g.pitch = bs + g.gap;
+    g.inner_v = g.gap + g.pitch * p.H;                        // ref:90-91 on the transposed (H, W) array
+    g.inner_h = g.gap + g.pitch * p.W;
+    g.pad_top = (size - g.inner_v) / 2;                       // ref:93-94
+    g.pad_left = (size - g.inner_h) / 2;
+    st_render_kernel<<<(unsigned)p.n, 256, 0, stream>>>(p, g, out);
+    count_launch();
+    return cudaGetLastError();
 }
 
 static inline unsigned cold_grid(long long n) { return (unsigned)((n + 127) / 128); }

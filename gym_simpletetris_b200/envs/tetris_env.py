@@ -185,7 +185,16 @@ class TetrisEnv(_Base):
         return obs
 
     def render(self, mode="human"):
-        raise NotImplementedError("render() is display code outside the step path (SURVEY.md section 8f)")
+        """mode='rgb_array': uint8 (160, 160, 3) image of the board with the active piece (tetris_env.py:458-462),
+        written by the `st_render` kernel.  mode='human' needs a pygame window (tetris_env.py:437-457): out of
+        scope here (display, not step path)."""
+        if mode == "rgb_array":
+            out = np.empty((160, 160, 3), dtype=np.uint8)
+            native.check(self._L.st_host_render(self._h, 1, 160, out.ctypes.data), "st_host_render")
+            return out
+        if mode == "human":
+            raise NotImplementedError("render('human') opens a pygame window; only 'rgb_array' is provided")
+        return None  # the reference defers to gym.Env.render, which does nothing for unknown modes
 
     def close(self):
         if getattr(self, "_h", None):
@@ -197,3 +206,19 @@ class TetrisEnv(_Base):
             self.close()
         except Exception:  # noqa: BLE001
             pass
+
+
+class TetrisEnvV26(TetrisEnv):
+    """The same env behind the gym >= 0.26 / gymnasium calling convention:
+    `reset(seed=None, options=None) -> (obs, info)` and `step(a) -> (obs, reward, terminated, truncated, info)`.
+    The reference only speaks the old API (tetris_env.py:397-411); nothing else changes."""
+
+    def reset(self, *, seed=None, options=None):  # noqa: ARG002
+        if seed is not None:
+            native.check(self._L.st_host_set_seed(self._h, int(seed) & (2 ** 64 - 1)), "st_host_set_seed")
+        obs, info = TetrisEnv.reset(self, return_info=True)
+        return obs, info
+
+    def step(self, action):
+        obs, reward, done, info = TetrisEnv.step(self, action)
+        return obs, reward, done, False, info  # Tetris never truncates: episodes end by topping out (ref:277-281)

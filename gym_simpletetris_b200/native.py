@@ -43,6 +43,7 @@ SYMBOLS = {
     "st_step": (C.c_int, [_CFG, _P, _P, _P, _P, _P, _P, _AUX, _I64, _P]),
     "st_step_many": (C.c_int, [_CFG, _P, _P, _I32, _P, _I64, _P, _P, _P, _I64, _AUX, _I64, _P]),
     "st_observe": (C.c_int, [_CFG, _P, _I32, _P, _I64, _P]),
+    "st_render": (C.c_int, [_CFG, _P, _I32, _I32, _P, _I64, _P]),
     "st_get_state": (C.c_int, [_CFG, _P, _P, _P, _I64, _P]),
     "st_set_state": (C.c_int, [_CFG, _P, _P, _P, _I64, _P]),
     "st_host_create": (_P, [_CFG, _I64]),
@@ -52,6 +53,8 @@ SYMBOLS = {
     "st_host_step": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "st_host_observe": (C.c_int, [_P, _I32, _P]),
     "st_host_set_zero_copy": (C.c_int, [_P, _I32]),
+    "st_host_set_seed": (C.c_int, [_P, C.c_uint64]),
+    "st_host_render": (C.c_int, [_P, _I32, _I32, _P]),
     "st_host_get_state": (C.c_int, [_P, _P, _P]),
     "st_host_set_state": (C.c_int, [_P, _P, _P]),
     "st_host_poll": (C.c_int, [_P, _P, _P]),

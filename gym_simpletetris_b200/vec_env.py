@@ -141,11 +141,24 @@ class VecEnv:
             C.byref(self._aux), n, self._stream()), "st_step_many")
         return obs, reward, done, self._info(info)
 
+    def capture_step(self):
+        """CUDA-graph the one-step launch: returns `GraphedStep`, whose call copies the
+        given actions into a static device buffer and replays the graph — no per-step ctypes/launch cost on the
+        host, so a device-resident policy can drive small batches at kernel rate."""
+        return GraphedStep(self)
+
     def observe(self, draw_piece=True):
         """_observation(engine.render()) (tetris_env.py:317-321, 413-433) of the current state, no step."""
         out = torch.empty_like(self.obs)
         self._check(self._L.st_observe(C.byref(self.cfg), self.state.data_ptr(), int(bool(draw_piece)),
                                        out.data_ptr(), self.num_envs, self._stream()), "st_observe")
+        return out
+
+    def render(self, size=160, draw_piece=True):
+        """Batched TetrisEnv.render('rgb_array') (tetris_env.py:458-462): uint8 [N, size, size, 3]."""
+        out = torch.empty((self.num_envs, size, size, 3), dtype=torch.uint8, device=self.device)
+        self._check(self._L.st_render(C.byref(self.cfg), self.state.data_ptr(), int(bool(draw_piece)), int(size),
+                                      out.data_ptr(), self.num_envs, self._stream()), "st_render")
         return out
 
     def close(self):
@@ -208,3 +221,25 @@ class VecEnv:
             s = all_reduce_sum(s)
         e, ln, li, sc = (int(v) for v in s.tolist())
         return {"episodes": e, "length_sum": ln, "lines_sum": li, "score_sum": sc}
+
+
+class GraphedStep:
+    """`g = env.capture_step(); obs, reward, done, info = g(actions)` — one CUDA-graph replay per step.
+    `g.actions` is the static uint8 [N] device buffer a policy kernel can write into directly (then call `g()`)."""
+
+    def __init__(self, env: VecEnv):
+        self.env = env
+        self.actions = torch.full((env.num_envs,), 6, dtype=torch.uint8, device=env.device)
+        side = torch.cuda.Stream(device=env.device)
+        side.wait_stream(torch.cuda.current_stream(env.device))
+        with torch.cuda.stream(side):
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=side):
+                self.out = env.step(self.actions)
+        torch.cuda.current_stream(env.device).wait_stream(side)
+
+    def __call__(self, actions=None):
+        if actions is not None:
+            self.actions.copy_(actions, non_blocking=True)
+        self.graph.replay()
+        return self.out

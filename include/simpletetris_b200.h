@@ -130,6 +130,11 @@ ST_API int st_step_many(const StConfig *cfg, void *state, const uint8_t *actions
  * draw_piece != 0; the bare board otherwise). */
 ST_API int st_observe(const StConfig *cfg, const void *state, int32_t draw_piece, float *obs, int64_t n, void *stream);
 
+/* TetrisEnv.render('rgb_array') (ref:458-462): engine.render() -> convert_grayscale(obs, size) ->
+ * convert_grayscale_rgb, uint8 out [n][size][size][3]; the reference uses size 160. */
+ST_API int st_render(const StConfig *cfg, const void *state, int32_t draw_piece, int32_t size, uint8_t *out,
+                     int64_t n, void *stream);
+
 /* ---- state injection / inspection (tests, checkpoints) -------------------------- */
 /* boards [n][W][H] uint8 (ref board[x,y]);  scalars [n][ST_UNPACKED_WORDS] int32: piece id (7 = none),
  * rotation (number of rotate_left applications, ref:22-26), anchor x, anchor y, lock-delay counter, time,
@@ -157,6 +162,9 @@ ST_API int st_host_observe(StHostEnv *h, int32_t draw_piece, float *obs);
 #define ST_ZC_SMALL 2   /* reward, done, info written straight to host memory */
 #define ST_ZC_OBS 4     /* observations written straight to host memory */
 ST_API int st_host_set_zero_copy(StHostEnv *h, int32_t mask);
+/* Re-key the piece stream (the `reset(seed=...)` of gym >= 0.26); effective from the next spawn. */
+ST_API int st_host_set_seed(StHostEnv *h, uint64_t seed);
+ST_API int st_host_render(StHostEnv *h, int32_t draw_piece, int32_t size, uint8_t *out);
 ST_API int st_host_get_state(StHostEnv *h, uint8_t *boards, int32_t *scalars);
 ST_API int st_host_set_state(StHostEnv *h, const uint8_t *boards, const int32_t *scalars);
 /* Reads and clears the sticky device error flag; stats_out (u64[ST_STATS_WORDS]) may be NULL. */

@@ -11,6 +11,8 @@ in place through oracle/ref_shim.py; nothing of it is copied.  Two fixtures:
                  reset on done.  Per step: reward (f64), done, the 13 info ints
                  (tetris_env.py:232-241) and a 64-bit digest of the float32
                  observation bytes; plus the digest of every reset observation.
+  render.npz     digests of `render('rgb_array')` (uint8 160x160x3, tetris_env.py:458-462) after reset and
+                 after every step of short rollouts (`--render-only` regenerates just this file).
   scenarios.npz  injected-board known answers: the reward table of SURVEY.md
                  B.2 for every flag combination used there, lock-delay traces
                  (B.3) and the edge cases of B.4, each as (initial board,
@@ -175,9 +177,50 @@ def make_scenarios():
     return sc
 
 
+RENDER_CASES = {
+    "default_10x20": dict(), "wide_20x40": dict(width=20, height=40), "odd_7x9": dict(width=7, height=9),
+    "narrow_4x20_ld2": dict(width=4, height=20, lock_delay=2), "sq_16x16": dict(width=16, height=16),
+}
+
+
+def render_rollout(kwargs, seed, T):
+    """TetrisEnv.render('rgb_array') (tetris_env.py:458-462) after reset and after every step."""
+    random.seed(seed)
+    env = make_reference_env(**kwargs)
+    pieces = record_pieces(env)
+    actions = actions_for(seed + 50, T)
+    env.reset()
+    first = env.render(mode="rgb_array")
+    assert first.dtype == np.uint8 and first.shape == (160, 160, 3)
+    dig, don = [np.frombuffer(hashlib.sha256(first.tobytes()).digest()[:8], dtype=np.uint64)[0]], []
+    for a in actions:
+        _, _, d, _ = env.step(int(a))
+        don.append(bool(d))
+        if d:
+            env.reset()
+        img = env.render(mode="rgb_array")
+        dig.append(np.frombuffer(hashlib.sha256(np.ascontiguousarray(img).tobytes()).digest()[:8], dtype=np.uint64)[0])
+    return dict(actions=actions, pieces=np.asarray(pieces, np.uint8), done=np.asarray(don, np.uint8),
+                digest=np.asarray(dig, np.uint64), first=first)
+
+
+def make_render():
+    out, meta = {}, {}
+    for name, kw in RENDER_CASES.items():
+        r = render_rollout(kw, 3, 400)
+        meta[name] = dict(kwargs=kw)
+        for k, v in r.items():
+            out[f"{name}/{k}"] = v
+    out["__meta__"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, "render.npz"), **out)
+    print("render cases:", len(meta))
+
+
 def main():
     ref = load_reference()
     assert ref.shape_names == SHAPE_NAMES
+    if "--render-only" in sys.argv:
+        return make_render()
     out = {}
     meta = {}
     for name, kw in CASES.items():
@@ -202,6 +245,7 @@ def main():
     out["__meta__"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
     np.savez_compressed(os.path.join(HERE, "scenarios.npz"), **out)
     print("scenarios:", len(meta))
+    make_render()
 
 
 if __name__ == "__main__":

@@ -267,3 +267,73 @@ def test_full_size_image_properties(st, n, kw):
     assert bool(((flat == 0) | (flat == 128) | (flat == 190)).all())
     assert torch.equal((flat == 190).sum(1).float(), cells * 9 * ch)  # 10x20 at 84: 3x3 blocks
     assert bool(((flat == 0).sum(1) == 3735 * ch).all())  # border pixels
+
+
+# ---- render('rgb_array') -----------------------------------------------------------
+REND = golden("render.npz")
+
+
+def digest_u8(a):
+    import hashlib
+
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a, dtype=np.uint8).tobytes()).digest()[:8], dtype=np.uint64)[0]
+
+
+@pytest.mark.parametrize("key", REND.keys())
+def test_render_rgb_array_matches_reference_fixture(st, key):
+    g = lambda f: REND.get(key, f)
+    env = st.make("SimpleTetris-v0", **REND.kwargs(key))
+    env.engine.set_pieces(g("pieces"))
+    env.reset()
+    img = env.render(mode="rgb_array")
+    assert img.dtype == np.uint8 and img.shape == (160, 160, 3)
+    assert np.array_equal(img, g("first"))
+    for t, a in enumerate(g("actions")):
+        _, _, d, _ = env.step(int(a))
+        assert d == bool(g("done")[t])
+        if d:
+            env.reset()
+        assert digest_u8(env.render(mode="rgb_array")) == g("digest")[t + 1], (key, t)
+
+
+def test_vecenv_render_matches_oracle_grayscale(st):
+    from oracle.oracle import convert_grayscale
+
+    for kw, size in ((dict(), 160), (dict(width=6, height=31), 96), (dict(width=20, height=40), 512)):
+        env = st.VecEnv(5, device="cuda:0", seed=9, lock_delay=1, **kw)
+        env.reset()
+        rs = np.random.RandomState(1)
+        for _ in range(30):
+            env.step(torch.from_numpy(rs.randint(0, 7, 5).astype(np.uint8)))
+        shown = env.observe(True).cpu().numpy()
+        img = env.render(size=size).cpu().numpy()
+        for e in range(5):
+            want = np.repeat(convert_grayscale(shown[e], size)[:, :, None], 3, axis=2)
+            assert np.array_equal(img[e], want)
+
+
+def test_graphed_step_equals_step(st):
+    kw = dict(reward_step=True, advanced_clears=True)
+    n, T = 200, 60
+    acts = np.random.RandomState(2).randint(0, 7, (T, n)).astype(np.uint8)
+    a = run_vec(st, n, acts, seed=12, **kw)
+    env = st.VecEnv(n, device="cuda:0", seed=12, **kw)
+    env.reset()
+    g = env.capture_step()
+    for t in range(T):
+        obs, r, d, info = g(torch.from_numpy(acts[t]).cuda())
+        assert np.array_equal(r.cpu().numpy(), a["reward"][t])
+        assert np.array_equal(d.cpu().numpy().astype(np.uint8), a["done"][t])
+    assert np.array_equal(obs.cpu().numpy().reshape(n, -1), a["obs"])
+
+
+def test_v26_api(st):
+    env, env2 = st.TetrisEnvV26(width=6, height=10), st.TetrisEnvV26(width=6, height=10)
+    (obs, info), (obs2, info2) = env.reset(seed=5), env2.reset(seed=5)
+    assert obs.shape == (6, 10) and info["time"] == 0 and info == info2
+    for a in [2, 0, 2, 4, 2, 2, 1, 2, 2, 2, 2, 2]:
+        out, out2 = env.step(a), env2.step(a)
+        assert len(out) == 5 and out[3] is False
+        assert np.array_equal(out[0], out2[0]) and out[1:] == out2[1:]  # same seed -> same piece stream
+        if out[2]:
+            env.reset(), env2.reset()

@@ -46,6 +46,12 @@ WORKLOADS = {
     "C5b": dict(n=65536, kw=dict(width=20, height=40),
                 desc="C5b: 65536 envs/GPU, wide board 40x20 (H=40, W=20), ram obs"),
 }
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE timed-region launch of the step kernel, from the
+# `ncu --set full` captures summarised in profiles/r1_<workload>_step_kernel_ncu_full.txt.  ncu flushes caches
+# before the single replayed launch and stops at kernel end, so writes still sitting in the 126 MB L2 are not
+# counted: the small ram workloads read their state from DRAM but their observations stay in L2.
+NCU_TRAFFIC_BYTES = {"C2": 440832 + 0, "C3": 6646016 + 8084480, "C4": 33316864 + 7380977000,
+                     "C5a": 19061504 + 11061187000, "C5b": 14519808 + 164066304}
 HEADLINE = "C2"
 L2_BYTES = 126 << 20
 
@@ -197,7 +203,9 @@ def time_workload(name, steps, warmup, rank, world, dist, burn_in=200):
         "value": n * world * steps / (total_ms * 1e-3), "ms_per_step": total_ms / steps,
         "launches": launches, "episodes_all_ranks": stats["episodes"],
         "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                     "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                     "frac": round(achieved / peak, 4), "traffic": NCU_TRAFFIC_BYTES.get(name),
+                     "traffic_note": "ncu dram bytes of one launch (L2-resident writes not included)",
+                     "algorithmic_bytes_per_launch": B * n, "peak_source": peak_src,
                      "kernel": f"st_main_kernel<{2 if kw.get('height', 20) > 31 else 1},"
                                f"{ {'ram': 0, 'grayscale': 1, 'rgb': 2}[kw.get('obs_type', 'ram')] },STEP>",
                      "algorithmic_bytes_per_env_step": B, "env_steps_per_launch": n,
@@ -206,6 +214,25 @@ def time_workload(name, steps, warmup, rank, world, dist, burn_in=200):
     del envs, actions, graphs
     torch.cuda.empty_cache()
     return res
+
+
+def write_only_ceiling_gbs():
+    """Practical ceiling of a store-only kernel: GB/s of a plain 4 GiB fill, best of 5."""
+    import torch
+
+    x = torch.empty(1 << 30, dtype=torch.float32, device="cuda")
+    best = 0.0
+    for i in range(7):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        x.fill_(128.0)
+        b.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            best = max(best, x.numel() * 4 / (a.elapsed_time(b) * 1e-3) / 1e9)
+    del x
+    torch.cuda.empty_cache()
+    return round(best, 1)
 
 
 def time_e2e(name, steps, warmup, rank, world, dist, zero_copy=None):
@@ -367,6 +394,7 @@ def main():
         r = time_workload(nm, args.mode_steps, max(3, min(args.warmup, 5)), rank, world, dist)
         r["e2e"] = time_e2e(nm, 5, 3, rank, world, dist) if WORKLOADS[nm]["n"] * algorithmic_bytes(WORKLOADS[nm]["kw"]) < (2 << 30) else None
         modes[nm] = r
+    fill_gbs = write_only_ceiling_gbs() if rank == 0 else None
     clocks = sampler.stop()
 
     cpu = None
@@ -391,6 +419,7 @@ def main():
                              "launching stream around them, barrier + synchronize on both sides; max over ranks"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": head["launches"], "roofline": head["roofline"],
         "cpu_baseline": cpu, "modes": modes,
+        "hbm_write_only_fill_gbs": fill_gbs,  # plain 4 GiB torch fill_ on this GPU: ceiling of a store-only kernel
     }
     print(json.dumps(line), flush=True)
 

@@ -7,7 +7,11 @@ namespace st {
 
 enum Mode : int { MODE_STEP = 0, MODE_RESET = 1, MODE_OBSERVE = 2 };
 
-constexpr int kWarpsPerCta = 8;       // one env per warp, 8 envs per CTA pass
+constexpr int kWarpsPerCta = 8;       // image modes: one env per warp, 8 envs per CTA
+#ifndef ST_RAM_WARPS
+#define ST_RAM_WARPS 4
+#endif
+constexpr int kRamWarpsPerCta = ST_RAM_WARPS;  // ram mode
 constexpr int kThreads = 32 * kWarpsPerCta;
 constexpr int kImage = 84;            // ref:426: _observation always renders at 84
 constexpr int kStateWords = 15;

@@ -16,8 +16,24 @@
 // slot, so a warp store covers 512 contiguous bytes.
 #include "st_internal.h"
 
+#include <cstdlib>
+
 namespace st {
 
+#ifndef ST_IMG_STORE
+#define ST_IMG_STORE 0
+#endif
+#ifndef ST_IMG_MINBLOCKS
+#define ST_IMG_MINBLOCKS 1
+#endif
+#ifndef ST_IMG_UNROLL
+#define ST_IMG_UNROLL 1
+#endif
+#ifndef ST_IMG_ORDER
+#define ST_IMG_ORDER 0
+#endif
+
+constexpr int kImgUnroll = ST_IMG_UNROLL;  // image-row loop unroll (tuning knob)
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int OFF = 4;  // board column x lives at bit x + OFF of a widened row
 
@@ -424,17 +440,24 @@ __device__ __forceinline__ ColSlot make_col_slot(int k, const Params &p)
 // The step / reset / observe kernel.  OBS: 0 ram, 1 grayscale, 2 rgb.  MODE is a template parameter so
 // that the step kernel carries no reset/observe code.
 // ---------------------------------------------------------------------------------------------
-template <int RPL, int OBS, int MODE, typename RowT>
-__global__ void __launch_bounds__(kThreads) st_main_kernel(const __grid_constant__ Params p)
-{
-    __shared__ __align__(16) uint32_t s_disp[kWarpsPerCta][32 * RPL];
-    __shared__ signed char s_rowy[OBS == 0 ? 1 : kImage];
-    __shared__ unsigned char s_active[kWarpsPerCta];
+// Warps (= envs) per CTA: image modes need 8 (252 writer threads); ram warps are independent, and smaller CTAs
+// spread a small batch more evenly over the 148 SMs.
+template <int OBS> struct Wpc { static constexpr int value = OBS == 0 ? kRamWarpsPerCta : kWarpsPerCta; };
 
+template <int RPL, int OBS, int MODE, typename RowT>
+__global__ void __launch_bounds__(32 * Wpc<OBS>::value, OBS == 0 ? 1 : ST_IMG_MINBLOCKS) st_main_kernel(const __grid_constant__ Params p)
+{
+    constexpr int WPC = Wpc<OBS>::value;
+    __shared__ __align__(16) uint32_t s_disp[WPC][32 * RPL];
+    __shared__ signed char s_rowy[OBS == 0 ? 1 : kImage];
+    __shared__ unsigned char s_active[WPC];
+
+    // Programmatic dependent launch: let the next step's grid start its prologue while this one runs ...
+    asm volatile("griddepcontrol.launch_dependents;");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int H = p.H;
     const int n = (int)p.n;
-    const int e = blockIdx.x * kWarpsPerCta + warp;  // this warp's env (launch_main keeps n below 2^31)
+    const int e = blockIdx.x * WPC + warp;  // this warp's env (launch_main keeps n below 2^31)
     const bool valid = e < n;
     if (OBS == 0 && !valid) return;  // ram warps never meet at a CTA barrier
     const RowT walls = (RowT)0xF | (~(RowT)0 << (p.W + OFF));
@@ -453,6 +476,8 @@ __global__ void __launch_bounds__(kThreads) st_main_kernel(const __grid_constant
         }
     }
 
+    // ... and do not touch global memory before the previous grid in the stream has completed and flushed.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     bool selected = valid;
     if (MODE == MODE_RESET && valid && p.mask && p.mask[e] == 0) selected = false;
     unsigned char *rec = p.state + (size_t)(valid ? e : 0) * (unsigned)p.stride;
@@ -479,7 +504,7 @@ __global__ void __launch_bounds__(kThreads) st_main_kernel(const __grid_constant
     float *rew_p = MODE == MODE_STEP ? p.reward + e : nullptr;
     uint8_t *done_p = MODE == MODE_STEP ? p.done + e : nullptr;
     int32_t *info_p = (MODE == MODE_STEP && p.info) ? p.info + (size_t)e * kStateWords + lane : nullptr;
-    float *obs_p = p.obs ? p.obs + (size_t)(OBS == 0 ? e : (int)blockIdx.x * kWarpsPerCta) * (unsigned)p.obs_elems : nullptr;
+    float *obs_p = p.obs ? p.obs + (size_t)(OBS == 0 ? e : (int)blockIdx.x * WPC) * (unsigned)p.obs_elems : nullptr;
     int action = 6;
     if (MODE == MODE_STEP && selected) action = *act_p;  // issued together with the state loads
     if (selected) pc = unpack_piece(get(sw, 0));
@@ -544,10 +569,38 @@ __global__ void __launch_bounds__(kThreads) st_main_kernel(const __grid_constant
             __syncthreads();
             if (threadIdx.x < KPR * NG) {
                 float4 *base = reinterpret_cast<float4 *>(obs_p) + slot_k;
+#if ST_IMG_ORDER == 1
+                // Board-row major: every board row y becomes `bs` identical image rows plus `gap` grid rows, so the
+                // four selects are done once per (env, y) and reused for pitch stores (closed form of ref:99-112).
+                const unsigned img4 = (unsigned)(p.obs_elems >> 2);
+                const int pitch = p.pitch, gap = p.gap, bs = pitch - gap, top = p.pad_top;
+                const float4 vgap = make_float4(cs.lo[0], cs.lo[1], cs.lo[2], cs.lo[3]);
+                const float4 vzero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+                for (int w = 0; w < WPC; ++w) {
+                    if (!s_active[w]) continue;
+                    float4 *img = base + (size_t)w * img4;
+                    for (int r = slot_g; r < top; r += NG) img[r * KPR] = vzero;                          // top border
+                    for (int r = top + p.inner_v + slot_g; r < kImage; r += NG) img[r * KPR] = vzero;   // bottom border
+                    for (int r = slot_g; r < gap; r += NG) img[(top + r) * KPR] = vgap;                   // first grid line
+                    for (int y = slot_g; y < H; y += NG) {
+                        const uint32_t b = s_disp[w][y];
+                        float4 v;
+                        v.x = (b & cs.mk[0]) ? cs.hi[0] : cs.lo[0];
+                        v.y = (b & cs.mk[1]) ? cs.hi[1] : cs.lo[1];
+                        v.z = (b & cs.mk[2]) ? cs.hi[2] : cs.lo[2];
+                        v.w = (b & cs.mk[3]) ? cs.hi[3] : cs.lo[3];
+                        float4 *rowp = img + (top + gap + y * pitch) * KPR;
+                        for (int r = 0; r < bs; ++r) rowp[r * KPR] = v;
+                        for (int r = bs; r < pitch; ++r) rowp[r * KPR] = vgap;
+                    }
+                }
+#else
+#pragma unroll kImgUnroll
                 for (int rho = slot_g; rho < kImage; rho += NG) {
                     const int code = s_rowy[rho];
 #pragma unroll
-                    for (int w = 0; w < kWarpsPerCta; ++w) {
+                    for (int w = 0; w < WPC; ++w) {
                         if (!s_active[w]) continue;
                         const uint32_t b = code >= 0 ? s_disp[w][code] : 0u;
                         float4 v;
@@ -556,9 +609,17 @@ __global__ void __launch_bounds__(kThreads) st_main_kernel(const __grid_constant
                         v.z = (b & cs.mk[2]) ? cs.hi[2] : cs.lo[2];
                         v.w = (b & cs.mk[3]) ? cs.hi[3] : cs.lo[3];
                         if (code == -2) v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        base[(size_t)w * (unsigned)(p.obs_elems >> 2) + rho * KPR] = v;
+                        float4 *dst = base + (size_t)w * (unsigned)(p.obs_elems >> 2) + rho * KPR;
+#if ST_IMG_STORE == 1
+                        __stcs(dst, v);  // streaming: written once, never re-read by this kernel
+#elif ST_IMG_STORE == 2
+                        __stwt(dst, v);
+#else
+                        *dst = v;
+#endif
                     }
                 }
+#endif
             }
             __syncthreads();
         }
@@ -708,11 +769,28 @@ static inline void count_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOM
 template <int RPL, int OBS, int MODE, typename RowT>
 static cudaError_t launch_t(const Params &p, cudaStream_t stream)
 {
-    const long long ngroups = (p.n + kWarpsPerCta - 1) / kWarpsPerCta;
+    constexpr int WPC = Wpc<OBS>::value;
+    const long long ngroups = (p.n + WPC - 1) / WPC;
     if (ngroups == 0) return cudaSuccess;
-    st_main_kernel<RPL, OBS, MODE, RowT><<<(unsigned)ngroups, kThreads, 0, stream>>>(p);
+    static const bool pdl = getenv("ST_B200_NO_PDL") == nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)ngroups);
+    cfg.blockDim = dim3(32 * WPC);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    if (OBS != 0) {  // experiment knob: unused dynamic shared memory caps the resident CTAs per SM
+        static const int dsmem = getenv("ST_B200_IMG_DSMEM") ? atoi(getenv("ST_B200_IMG_DSMEM")) : 0;
+        if (dsmem > 0) {
+            cudaFuncSetAttribute(st_main_kernel<RPL, OBS, MODE, RowT>, cudaFuncAttributeMaxDynamicSharedMemorySize, dsmem);
+            cfg.dynamicSmemBytes = (size_t)dsmem;
+        }
+    }
     count_launch();
-    return cudaGetLastError();
+    return cudaLaunchKernelEx(&cfg, st_main_kernel<RPL, OBS, MODE, RowT>, p);
 }
 
 template <int RPL, int OBS, typename RowT>

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libsimpletetris_b200.so")
+SO_PATH = os.environ.get("ST_B200_LIB") or os.path.join(_HERE, "libsimpletetris_b200.so")  # override: kernel experiments
 
 ST_STATE_WORDS = 15
 ST_INFO_WORDS = 15

@@ -73,6 +73,12 @@ class VecEnv:
         self.stats = torch.zeros(ST_STATS_WORDS, dtype=torch.int64, device=dev)
         self._queue = None
         self._aux = StAux(None, 0, 0, self.err.data_ptr(), self.stats.data_ptr())
+        # per-step host cost matters for small batches: everything constant across steps is bound once
+        self._cfg_ref, self._aux_ref = C.byref(self.cfg), C.byref(self._aux)
+        self._info_views = self._info(self.info_buf)
+        self._ptrs = (self.state.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
+                      self.info_buf.data_ptr() if self.info_buf is not None else None)
+        self._st_step = self._L.st_step
         self._check(self._L.st_init(C.byref(self.cfg), self.state.data_ptr(), n, self._stream()), "st_init")
 
     # ---- plumbing ----
@@ -84,12 +90,15 @@ class VecEnv:
         native.check(rc, what)
 
     def _actions(self, actions, shape):
+        if (torch.is_tensor(actions) and actions.dtype == torch.uint8 and actions.device == self.device
+                and actions.shape == shape and actions.is_contiguous()):
+            return actions
         if not torch.is_tensor(actions):
             actions = torch.as_tensor(np.asarray(actions))
         if actions.dtype != torch.uint8:
             actions = actions.to(torch.uint8)
         actions = actions.to(self.device, non_blocking=True).contiguous()
-        if tuple(actions.shape) != shape:
+        if tuple(actions.shape) != tuple(shape):
             raise ValueError(f"actions must have shape {shape}, got {tuple(actions.shape)}")
         return actions
 
@@ -116,11 +125,12 @@ class VecEnv:
         """TetrisEnv.step (tetris_env.py:397-403) for N envs: (obs [N,...] f32, reward [N] f32, done [N] bool, info).
         The returned tensors are the env's own buffers and are overwritten by the next call."""
         a = self._actions(actions, (self.num_envs,))
-        self._check(self._L.st_step(
-            C.byref(self.cfg), self.state.data_ptr(), a.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(),
-            self.done.data_ptr(), self.info_buf.data_ptr() if self.info_buf is not None else None,
-            C.byref(self._aux), self.num_envs, self._stream()), "st_step")
-        return self.obs, self.reward, self.done, self._info()
+        state, obs, reward, done, info = self._ptrs
+        rc = self._st_step(self._cfg_ref, state, a.data_ptr(), obs, reward, done, info, self._aux_ref, self.num_envs,
+                           torch.cuda.current_stream(self.device).cuda_stream)
+        if rc:
+            self._check(rc, "st_step")
+        return self.obs, self.reward, self.done, self._info_views
 
     def step_many(self, actions, rollout_obs=False, rollout_info=False):
         """T steps in one launch.  actions [T, N].  Returns (obs, reward [T,N], done [T,N], info): obs is

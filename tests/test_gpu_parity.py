@@ -337,3 +337,69 @@ def test_v26_api(st):
         assert np.array_equal(out[0], out2[0]) and out[1:] == out2[1:]  # same seed -> same piece stream
         if out[2]:
             env.reset(), env2.reset()
+
+
+# ---- geometry sweep: every observation writer against the oracle's np.repeat/np.insert restatement ---------
+def test_observation_writers_on_random_geometries(st):
+    from oracle.oracle import convert_grayscale
+
+    rs = np.random.RandomState(123)
+    geoms = [(1, 1), (32, 63), (2, 31), (25, 32), (24, 4), (3, 41), (10, 42), (16, 20), (31, 5)]
+    geoms += [(int(rs.randint(1, 33)), int(rs.randint(1, 64))) for _ in range(16)]
+    n = 6
+    for (w, h) in geoms:
+        boards = (rs.rand(n, w, h) < 0.45).astype(np.uint8)
+        for ot in ("ram", "grayscale", "rgb"):
+            env = st.VecEnv(n, width=w, height=h, obs_type=ot, device="cuda:0")
+            env.reset()
+            env.set_state(boards=boards)
+            got = env.observe(draw_piece=False).cpu().numpy()
+            for e in range(n):
+                if ot == "ram":
+                    want = boards[e].astype(np.float32)
+                else:
+                    g = convert_grayscale(boards[e], 84).astype(np.float32)
+                    want = g if ot == "grayscale" else np.repeat(g[:, :, None], 3, axis=2)
+                assert np.array_equal(got[e], want), (w, h, ot, e)
+            b2, _ = env.get_state()
+            assert np.array_equal(b2.cpu().numpy(), boards)  # set_state / get_state round trip
+        size = int(rs.choice([84, 100, 160, 257]))
+        gap = size // 100 + 1
+        if (size - 2 * gap) // max(w, h) - gap >= 0:
+            img = env.render(size=size, draw_piece=False).cpu().numpy()
+            for e in range(n):
+                assert np.array_equal(img[e, :, :, 1], convert_grayscale(boards[e], size)), (w, h, size)
+
+
+def test_piece_stream_follows_reference_weighting(st):
+    """_choose_shape (tetris_env.py:183-191): first piece uniform over 7 (all weights 5); lifetime counts self-balance
+    (max - min stays tiny because the weight of a lagging piece grows)."""
+    n = 70000
+    env = st.VecEnv(n, width=4, height=6, device="cuda:0", seed=99)
+    env.reset()
+    _, sc = env.get_state()
+    first = torch.bincount(sc[:, 0].long(), minlength=7).cpu().numpy().astype(np.float64)
+    chi2 = float(((first - n / 7) ** 2 / (n / 7)).sum())
+    assert chi2 < 22.46, (chi2, first)  # chi-square, 6 dof, p = 0.001
+    hard = torch.full((n,), 2, dtype=torch.uint8, device="cuda")
+    for _ in range(400):
+        env.step(hard)
+    _, sc = env.get_state()
+    counts = sc[:, 11:18].long()
+    assert int(counts.sum(1).min()) > 150  # ~1 piece per 2 steps on a 4x6 board
+    spread = (counts.max(1).values - counts.min(1).values)
+    # a NumPy simulation of the rule with an ideal uniform source gives mean 5.2, max 12 over 3000 envs x 200 pieces;
+    # uniform piece draws (no weighting) would give a spread of about 17 at this length
+    assert 4.0 < float(spread.float().mean()) < 6.5 and int(spread.max()) <= 16
+    # second-piece law for envs whose first piece was T (id 0): weights (5,6,6,6,6,6,6)/41
+    env2 = st.VecEnv(n, width=4, height=6, device="cuda:0", seed=7)
+    env2.reset()
+    _, s0 = env2.get_state()
+    env2.reset()
+    _, s1 = env2.get_state()
+    sel = s0[:, 0] == 0
+    second = torch.bincount(s1[sel, 0].long(), minlength=7).cpu().numpy().astype(np.float64)
+    m = float(sel.sum())
+    expect = np.array([5, 6, 6, 6, 6, 6, 6]) / 41 * m
+    chi2 = float(((second - expect) ** 2 / expect).sum())
+    assert chi2 < 22.46, (chi2, second, expect)

@@ -277,6 +277,23 @@ static void *mapped_alias(StHostEnv *h, int slot, const void *host)
     return dev;
 }
 
+void *st_host_alloc_pinned(size_t bytes)
+{
+    void *ptr = nullptr;
+    cudaError_t e = cudaHostAlloc(&ptr, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped);
+    if (e != cudaSuccess) {
+        fail_cuda(e, "cudaHostAlloc");
+        return nullptr;
+    }
+    memset(ptr, 0, bytes);
+    return ptr;
+}
+
+void st_host_free_pinned(void *ptr)
+{
+    if (ptr) cudaFreeHost(ptr);
+}
+
 int st_host_set_seed(StHostEnv *h, uint64_t seed)
 {
     if (!h) return fail(ST_E_INVALID, "NULL handle%s");

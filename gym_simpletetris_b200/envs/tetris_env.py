@@ -95,12 +95,14 @@ class EngineView:
         s[0, 0] = shape_names.index(name) if isinstance(name, str) else int(name)
         s[0, 1], s[0, 2], s[0, 3] = rot, self.width // 2 if x is None else x, y
         native.check(self._env._L.st_host_set_state(self._env._h, None, s.ctypes.data), "st_host_set_state")
+        self._env._was_reset = True  # there is a piece now
 
     def set_pieces(self, pieces):
         """Inject the lifetime piece sequence (the `_choose_shape` replacement used by parity tests)."""
         q = np.asarray([shape_names.index(p) if isinstance(p, str) else int(p) for p in pieces], dtype=np.uint8)
         native.check(self._env._L.st_host_set_piece_queue(self._env._h, q.ctypes.data, len(q)),
                      "st_host_set_piece_queue")
+        self._env._queue_set = True
 
     def get_info(self):
         return self._env._get_info()
@@ -141,7 +143,23 @@ class TetrisEnv(_Base):
         if obs_type in ("ram", "grayscale", "rgb"):
             self.observation_space = Box(0, 1, shape=shp, dtype=np.float32)
         self._obs_shape = shp
-        self._info_buf = np.zeros((1, native.ST_INFO_WORDS), dtype=np.int32)
+        # One page-locked block for everything a step moves: the kernel reads the action from it and writes
+        # obs / reward / done / info into it directly (no staging copies), so a step is one launch + one sync.
+        nobs = int(np.prod(shp))
+        nbytes = nobs * 4 + native.ST_INFO_WORDS * 4 + 16
+        self._pinned = self._L.st_host_alloc_pinned(nbytes)
+        if not self._pinned:
+            raise RuntimeError("st_host_alloc_pinned failed: " + self._L.st_last_error().decode())
+        buf = (C.c_uint8 * nbytes).from_address(self._pinned)
+        self._obs_buf = np.frombuffer(buf, dtype=np.float32, count=nobs, offset=0).reshape(shp)
+        self._info_buf = np.frombuffer(buf, dtype=np.int32, count=native.ST_INFO_WORDS, offset=nobs * 4).reshape(1, -1)
+        tail = nobs * 4 + native.ST_INFO_WORDS * 4
+        self._reward_buf = np.frombuffer(buf, dtype=np.float32, count=1, offset=tail)
+        self._done_buf = np.frombuffer(buf, dtype=np.uint8, count=1, offset=tail + 4)
+        self._act_buf = np.frombuffer(buf, dtype=np.uint8, count=1, offset=tail + 8)
+        self._ptr = {k: int(getattr(self, "_" + k + "_buf").ctypes.data) for k in ("obs", "info", "reward", "done", "act")}
+        self._was_reset = False
+        self._queue_set = False
         self.engine = EngineView(self)
 
     def _get_info(self):
@@ -154,19 +172,21 @@ class TetrisEnv(_Base):
     def step(self, action):
         if isinstance(action, (bool, np.bool_)) or int(action) != action or not 0 <= int(action) <= 6:
             raise KeyError(action)  # value_action_map lookup, tetris_env.py:245
-        a = np.asarray([int(action)], dtype=np.uint8)
-        obs = np.empty(self._obs_shape, dtype=np.float32)
-        reward = np.zeros(1, dtype=np.float32)
-        done = np.zeros(1, dtype=np.uint8)
-        native.check(self._L.st_host_step(self._h, a.ctypes.data, obs.ctypes.data, reward.ctypes.data,
-                                          done.ctypes.data, self._info_buf.ctypes.data), "st_host_step")
-        err = C.c_int32(0)
-        native.check(self._L.st_host_poll(self._h, C.byref(err), None), "st_host_poll")
-        if err.value & 4:
+        if not self._was_reset:
             raise TypeError("step() called before reset(): the engine has no piece (tetris_env.py:170-172)")
-        if err.value & 1:
-            raise IndexError("injected piece queue exhausted")
-        r = float(reward[0])
+        self._act_buf[0] = int(action)
+        p = self._ptr
+        rc = self._L.st_host_step(self._h, p["act"], p["obs"], p["reward"], p["done"], p["info"])
+        if rc:
+            native.check(rc, "st_host_step")
+        if self._queue_set:  # only an injected piece queue can raise a device-side error here
+            err = C.c_int32(0)
+            native.check(self._L.st_host_poll(self._h, C.byref(err), None), "st_host_poll")
+            if err.value & 1:
+                raise IndexError("injected piece queue exhausted")
+        obs = self._obs_buf.copy()  # the reference returns a fresh array every step (tetris_env.py:400)
+        r = float(self._reward_buf[0])
+        done = self._done_buf
         i = self._info_buf[0]
         info = {"time": int(i[2]), "current_piece": shape_names[i[0]], "score": int(i[3]),
                 "lines_cleared": int(i[4]), "holes": int(i[5]), "deaths": int(i[7]),
@@ -176,6 +196,7 @@ class TetrisEnv(_Base):
     def reset(self, return_info=False):
         obs = np.empty(self._obs_shape, dtype=np.float32)
         native.check(self._L.st_host_reset(self._h, None, obs.ctypes.data), "st_host_reset")
+        self._was_reset = True
         return (obs, self._get_info()) if return_info else obs
 
     def _observation(self):
@@ -200,6 +221,10 @@ class TetrisEnv(_Base):
         if getattr(self, "_h", None):
             self._L.st_host_destroy(self._h)
             self._h = None
+        if getattr(self, "_pinned", None):
+            self._obs_buf = self._info_buf = self._reward_buf = self._done_buf = self._act_buf = None
+            self._L.st_host_free_pinned(self._pinned)
+            self._pinned = None
 
     def __del__(self):
         try:

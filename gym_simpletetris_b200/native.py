@@ -54,6 +54,8 @@ SYMBOLS = {
     "st_host_observe": (C.c_int, [_P, _I32, _P]),
     "st_host_set_zero_copy": (C.c_int, [_P, _I32]),
     "st_host_set_seed": (C.c_int, [_P, C.c_uint64]),
+    "st_host_alloc_pinned": (_P, [C.c_size_t]),
+    "st_host_free_pinned": (None, [_P]),
     "st_host_render": (C.c_int, [_P, _I32, _I32, _P]),
     "st_host_get_state": (C.c_int, [_P, _P, _P]),
     "st_host_set_state": (C.c_int, [_P, _P, _P]),

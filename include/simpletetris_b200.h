@@ -162,6 +162,10 @@ ST_API int st_host_observe(StHostEnv *h, int32_t draw_piece, float *obs);
 #define ST_ZC_SMALL 2   /* reward, done, info written straight to host memory */
 #define ST_ZC_OBS 4     /* observations written straight to host memory */
 ST_API int st_host_set_zero_copy(StHostEnv *h, int32_t mask);
+/* Page-locked, device-mapped host memory for the buffers of st_host_step (NumPy callers have no pinned
+ * allocator of their own); zero-filled.  NULL on failure. */
+ST_API void *st_host_alloc_pinned(size_t bytes);
+ST_API void st_host_free_pinned(void *ptr);
 /* Re-key the piece stream (the `reset(seed=...)` of gym >= 0.26); effective from the next spawn. */
 ST_API int st_host_set_seed(StHostEnv *h, uint64_t seed);
 ST_API int st_host_render(StHostEnv *h, int32_t draw_piece, int32_t size, uint8_t *out);

@@ -68,6 +68,7 @@ int make_params(const StConfig *c, const StAux *aux, int64_t n, st::Params *out)
     p.pad_top = (size - p.inner_v) / 2;
     p.pad_left = (size - p.inner_h) / 2;
     p.inv_h20 = ((1u << 20) + c->height - 1) / c->height;
+    p.inv_sw20 = ((1u << 20) + (p.stride >> 2) - 1) / (p.stride >> 2);
     p.inv_hq20 = (c->height % 4 == 0) ? ((1u << 20) + c->height / 4 - 1) / (c->height / 4) : 0;
     if (aux) {
         p.queue = aux->piece_queue;
@@ -145,6 +146,7 @@ int st_step_many(const StConfig *cfg, void *state, const uint8_t *actions, int32
     if (int rc = make_params(cfg, aux, n, &p)) return rc;
     if (n && (!state || !actions || !reward || !done)) return fail(ST_E_INVALID, "state/actions/reward/done is NULL%s");
     if (T < 1) return fail(ST_E_INVALID, "T < 1%s");
+    if (((uintptr_t)state | (uintptr_t)obs) & 15) return fail(ST_E_INVALID, "state and obs must be 16-byte aligned%s");
     if (int rc = use_device(cfg)) return rc;
     p.state = (unsigned char *)state;
     p.actions = actions;

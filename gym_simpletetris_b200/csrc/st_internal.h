@@ -33,6 +33,7 @@ struct Params {
     int pitch, gap, inner_v, inner_h, pad_top, pad_left;
     uint32_t inv_h20;   // ceil(2^20 / H)      : i / H      for i < 2048
     uint32_t inv_hq20;  // ceil(2^20 / (H/4))  : q / (H/4)  when H % 4 == 0
+    uint32_t inv_sw20;  // ceil(2^20 / (stride/4)) : word index -> record, thread-per-env kernel
     // buffers
     unsigned char *state;
     const uint8_t *actions;
@@ -50,6 +51,7 @@ struct Params {
     long long obs_t_stride, info_t_stride;
     int mode;
     int draw_piece;
+    int tpe_epw;  // thread-per-env kernel: envs per warp
 };
 
 cudaError_t launch_main(const Params &p, int obs_type, cudaStream_t stream);

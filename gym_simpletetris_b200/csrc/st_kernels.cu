@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(32 * Wpc<OBS>::value, OBS == 0 ? 1 : ST_IMG_MI
         }
         if (OBS == 0) {
             __syncwarp();
-            if (obs_p) write_ram(s_disp[warp], obs_p, p, lane);
+            if (selected && obs_p) write_ram(s_disp[warp], obs_p, p, lane);  // unselected (masked-out) envs keep their obs
             __syncwarp();
         } else {
             if (lane == 0) s_active[warp] = selected && obs_p;
@@ -793,6 +793,10 @@ static cudaError_t launch_t(const Params &p, cudaStream_t stream)
     return cudaLaunchKernelEx(&cfg, st_main_kernel<RPL, OBS, MODE, RowT>, p);
 }
 
+}  // namespace st
+#include "st_kernels_tpe.cuh"
+namespace st {
+
 template <int RPL, int OBS, typename RowT>
 static cudaError_t launch_mode(const Params &p, cudaStream_t stream)
 {
@@ -817,6 +821,13 @@ static cudaError_t launch_obs(const Params &p, cudaStream_t stream)
 cudaError_t launch_main(const Params &p, int obs_type, cudaStream_t stream)
 {
     if (p.n >= (1ll << 31) - 8) return cudaErrorInvalidValue;
+    if (tpe_eligible(p, obs_type)) {
+        // ST_B200_RAM_PATH = warp | thread | auto (default): thread-per-env from tpe_min_envs() envs up, where the
+        // warp-per-env kernel is issue-bound; below that a warp per env has the shorter critical path
+        const char *path = getenv("ST_B200_RAM_PATH");
+        const bool force_thread = path && path[0] == 't', force_warp = path && path[0] == 'w';
+        if (force_thread || (!force_warp && p.n >= tpe_min_envs(p))) return launch_tpe(p, stream);
+    }
     switch (obs_type) {
     case 0: return launch_obs<0>(p, stream);
     case 1: return launch_obs<1>(p, stream);

@@ -21,6 +21,21 @@ def info_row(info):
             info["holes"], info["deaths"]] + [info["statistics"][n] for n in SHAPE_NAMES]
 
 
+@pytest.fixture(autouse=True, params=["auto", "thread"])
+def ram_path(request):
+    """Every test runs twice: with the default kernel choice (warp-per-env below 16384 envs) and with the
+    thread-per-env ram kernel forced (ST_B200_RAM_PATH is read by the library at every launch)."""
+    import os
+
+    old = os.environ.get("ST_B200_RAM_PATH")
+    os.environ["ST_B200_RAM_PATH"] = request.param
+    yield request.param
+    if old is None:
+        os.environ.pop("ST_B200_RAM_PATH", None)
+    else:
+        os.environ["ST_B200_RAM_PATH"] = old
+
+
 @pytest.fixture(scope="module")
 def st():
     import gym_simpletetris_b200 as st
@@ -164,6 +179,9 @@ def test_masked_reset_and_no_autoreset(st):
     mask = torch.zeros(n, dtype=torch.uint8)
     mask[::2] = 1
     before = env.obs.clone()
+    other = st.VecEnv(64, width=7, height=9, device="cuda:0")  # unrelated launches in between: whatever a
+    other.reset()                                              # masked-out env leaves in on-chip memory changes
+    other.step(torch.zeros(64, dtype=torch.uint8))
     o = env.reset(mask)
     assert bool((o[::2] == 0).all()) and torch.equal(o[1::2], before[1::2])
     obs, r, d, info = env.step(hard)

@@ -50,8 +50,8 @@ WORKLOADS = {
 # `ncu --set full` captures summarised in profiles/r1_<workload>_step_kernel_ncu_full.txt.  ncu flushes caches
 # before the single replayed launch and stops at kernel end, so writes still sitting in the 126 MB L2 are not
 # counted: the small ram workloads read their state from DRAM but their observations stay in L2.
-NCU_TRAFFIC_BYTES = {"C2": 440832 + 0, "C3": 6646016 + 8084480, "C4": 33316864 + 7380977000,
-                     "C5a": 19061504 + 11061187000, "C5b": 14519808 + 164066304}
+NCU_TRAFFIC_BYTES = {"C2": 440576 + 0, "C3": 6670592 + 7860736, "C4": 27191808 + 7383049000,
+                     "C5a": 19105536 + 11061010000, "C5b": 14545920 + 171609344}
 HEADLINE = "C2"
 L2_BYTES = 126 << 20
 
@@ -195,6 +195,11 @@ def time_workload(name, steps, warmup, rank, world, dist, burn_in=200):
     for env in envs:
         assert env.poll_errors() == 0
         stats["episodes"] += env.episode_stats(reduce=True)["episodes"]
+    import ctypes
+
+    from gym_simpletetris_b200 import native
+
+    kernel_name = native.lib().st_step_kernel_name(ctypes.byref(envs[0].cfg), n).decode()
     peak, peak_src = measured_peak()
     kernel_ms = rank_ms / steps
     achieved = B * n / (kernel_ms * 1e-3) / 1e9
@@ -206,8 +211,7 @@ def time_workload(name, steps, warmup, rank, world, dist, burn_in=200):
                      "frac": round(achieved / peak, 4), "traffic": NCU_TRAFFIC_BYTES.get(name),
                      "traffic_note": "ncu dram bytes of one launch (L2-resident writes not included)",
                      "algorithmic_bytes_per_launch": B * n, "peak_source": peak_src,
-                     "kernel": f"st_main_kernel<{2 if kw.get('height', 20) > 31 else 1},"
-                               f"{ {'ram': 0, 'grayscale': 1, 'rgb': 2}[kw.get('obs_type', 'ram')] },STEP>",
+                     "kernel": kernel_name,
                      "algorithmic_bytes_per_env_step": B, "env_steps_per_launch": n,
                      "avg_launch_ms": round(kernel_ms, 6)},
     }

@@ -511,6 +511,13 @@ int st_host_poll(StHostEnv *h, int32_t *error_flag_out, unsigned long long *stat
     return 0;
 }
 
+const char *st_step_kernel_name(const StConfig *cfg, int64_t n)
+{
+    st::Params p;
+    if (make_params(cfg, nullptr, n, &p)) return "";
+    return st::step_kernel_name(p, cfg->obs_type);
+}
+
 const char *st_last_error(void) { return g_err; }
 int st_abi_version(void) { return ST_ABI_VERSION; }
 unsigned long long st_launch_count(void) { return st::launch_count(); }

@@ -59,6 +59,7 @@ cudaError_t launch_init(const Params &p, cudaStream_t stream);
 cudaError_t launch_get_state(const Params &p, uint8_t *boards, int32_t *scalars, cudaStream_t stream);
 cudaError_t launch_set_state(const Params &p, const uint8_t *boards, const int32_t *scalars, cudaStream_t stream);
 cudaError_t launch_render(const Params &p, int size, uint8_t *out, cudaStream_t stream);
+const char *step_kernel_name(const Params &p, int obs_type);
 unsigned long long launch_count();
 
 }  // namespace st

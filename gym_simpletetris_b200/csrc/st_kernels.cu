@@ -836,6 +836,18 @@ cudaError_t launch_main(const Params &p, int obs_type, cudaStream_t stream)
     return cudaErrorInvalidValue;
 }
 
+// Which kernel a single-step launch of this configuration runs (for reports and profiles).
+const char *step_kernel_name(const Params &p, int obs_type)
+{
+    Params q = p;
+    q.mode = MODE_STEP;
+    q.T = 1;
+    const char *path = getenv("ST_B200_RAM_PATH");
+    const bool force_thread = path && path[0] == 't', force_warp = path && path[0] == 'w';
+    if (tpe_eligible(q, obs_type) && (force_thread || (!force_warp && q.n >= tpe_min_envs(q)))) return "st_step_tpe_kernel";
+    return obs_type == 0 ? "st_main_kernel<ram,STEP>" : obs_type == 1 ? "st_main_kernel<grayscale,STEP>" : "st_main_kernel<rgb,STEP>";
+}
+
 cudaError_t launch_render(const Params &p, int size, uint8_t *out, cudaStream_t stream)
 {
     if (p.n == 0) return cudaSuccess;

@@ -208,15 +208,14 @@ __device__ __forceinline__ void tpe_engine_step(const TpeRec<RowT, ROWS16> &rec,
     int y = pc.y;
     int ld = (int)rec.w[1];
     bool grounded;
-    if (action == 2) {  // hard_drop (ref:54-59): slide a 4-row window down until the next height collides
-        int Yt = y + 1 + pr.minj;  // top piece row at the candidate anchor y + 1
-        RowT r0 = rec.widened(Yt, H, walls), r1 = rec.widened(Yt + 1, H, walls), r2w = rec.widened(Yt + 2, H, walls),
-             r3 = rec.widened(Yt + 3, H, walls);
-        while (((pr.m[0] & r0) | (pr.m[1] & r1) | (pr.m[2] & r2w) | (pr.m[3] & r3)) == 0) {
-            ++y; ++Yt;
-            r0 = r1; r1 = r2w; r2w = r3;
-            r3 = rec.widened(Yt + 3, H, walls);
+    if (action == 2) {  // hard_drop (ref:54-59): first colliding anchor below, four candidates per window
+        uint32_t c4 = cm >> 1;  // anchors y+1 .. y+3 are already known
+        int ya = y + 1;
+        while (c4 == 0u) {      // ends at the floor at the latest (rows >= H collide with everything)
+            ya += (ya == y + 1) ? 3 : 4;
+            c4 = tpe_collisions(rec, pr, ya, H, walls);
         }
+        y = ya + (__ffs((int)c4) - 1) - 1;
         grounded = true;  // gravity (ref:247) cannot move it further, so step_reset does not fire
     } else {
         int d = 0;
@@ -342,15 +341,16 @@ __global__ void __launch_bounds__(32 * kTpeWarps) st_step_tpe_kernel(const __gri
             if (q < nq) {
                 for (int r = 0; r < nvalid; ++r) {
                     const uint32_t *rw = recs + r * pitch + kStateWords;
-                    uint32_t a, b, c, d;
-                    if (ROWS16) {
-                        const uint32_t w01 = rw[2 * yq], w23 = rw[2 * yq + 1];
-                        a = w01 & 0xffffu; b = w01 >> 16; c = w23 & 0xffffu; d = w23 >> 16;
+                    float4 v;
+                    if (ROWS16) {  // two 16-bit rows per word: test bit x and bit x + 16 in place
+                        const uint32_t w01 = rw[2 * yq], w23 = rw[2 * yq + 1], bith = bit << 16;
+                        v = make_float4((w01 & bit) ? 1.0f : 0.0f, (w01 & bith) ? 1.0f : 0.0f,
+                                        (w23 & bit) ? 1.0f : 0.0f, (w23 & bith) ? 1.0f : 0.0f);
                     } else {
-                        a = rw[4 * yq]; b = rw[4 * yq + 1]; c = rw[4 * yq + 2]; d = rw[4 * yq + 3];
+                        v = make_float4((rw[4 * yq] & bit) ? 1.0f : 0.0f, (rw[4 * yq + 1] & bit) ? 1.0f : 0.0f,
+                                        (rw[4 * yq + 2] & bit) ? 1.0f : 0.0f, (rw[4 * yq + 3] & bit) ? 1.0f : 0.0f);
                     }
-                    o4[r * nq + q] = make_float4((a & bit) ? 1.0f : 0.0f, (b & bit) ? 1.0f : 0.0f,
-                                                 (c & bit) ? 1.0f : 0.0f, (d & bit) ? 1.0f : 0.0f);
+                    o4[r * nq + q] = v;
                 }
             }
         }

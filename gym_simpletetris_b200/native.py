@@ -61,6 +61,7 @@ SYMBOLS = {
     "st_host_set_state": (C.c_int, [_P, _P, _P]),
     "st_host_poll": (C.c_int, [_P, _P, _P]),
     "st_last_error": (C.c_char_p, []),
+    "st_step_kernel_name": (C.c_char_p, [_CFG, _I64]),
     "st_abi_version": (C.c_int, []),
     "st_launch_count": (C.c_uint64, []),
 }

@@ -176,6 +176,9 @@ ST_API int st_host_poll(StHostEnv *h, int32_t *error_flag_out, unsigned long lon
 
 /* ---- misc ------------------------------------------------------------------------- */
 ST_API const char *st_last_error(void);
+/* Name of the kernel a single-step launch of (cfg, n) runs: ram mode switches from the warp-per-env kernel to the
+ * thread-per-env kernel for large batches (for reports and profiles). */
+ST_API const char *st_step_kernel_name(const StConfig *cfg, int64_t n);
 ST_API int st_abi_version(void);
 /* Number of kernels this library has launched in this process (all threads). */
 ST_API unsigned long long st_launch_count(void);

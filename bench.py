@@ -93,6 +93,26 @@ class ClockSampler:
         except Exception:  # noqa: BLE001
             self.nv = None
 
+    def _smi(self):  # fallback when pynvml is not importable: one nvidia-smi query per sample
+        import subprocess
+
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                f = [x.strip() for x in out.split(",")]
+                self.samples.append(int(f[0]))
+                self.max_mhz = int(f[1])
+                for nm, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.2)
+
     def _run(self):
         while not self._stop.is_set():
             try:
@@ -106,9 +126,8 @@ class ClockSampler:
             self._stop.wait(0.02)
 
     def start(self):
-        if self.nv:
-            self._thr = threading.Thread(target=self._run, daemon=True)
-            self._thr.start()
+        self._thr = threading.Thread(target=self._run if self.nv else self._smi, daemon=True)
+        self._thr.start()
 
     def stop(self):
         self._stop.set()

@@ -228,6 +228,7 @@ def test_observe_matches_step_obs(st):
     (4096, dict(reward_step=True, advanced_clears=True)),
     (65536, dict(penalise_height_increase=True, penalise_holes_increase=True, lock_delay=3, step_reset=True)),
     (65536, dict(width=20, height=40)),
+    (1048576, dict(reward_step=True)),
 ])
 def test_full_size_ram_properties(st, n, kw):
     from oracle.oracle import OracleEnv
@@ -235,8 +236,8 @@ def test_full_size_ram_properties(st, n, kw):
     env = st.VecEnv(n, device="cuda:0", seed=2, **kw)
     env.reset()
     g = torch.Generator(device="cuda").manual_seed(0)
-    T = 120
-    sample = torch.arange(0, n, n // 16, device="cuda")
+    T = 120 if n <= 65536 else 40
+    sample = torch.cat([torch.arange(0, n, n // 16, device="cuda"), torch.tensor([n - 1], device="cuda")])
     episodes = torch.zeros(n, dtype=torch.int64, device="cuda")
     trace = []
     for t in range(T):

@@ -23,6 +23,9 @@ namespace st {
 #ifndef ST_IMG_STORE
 #define ST_IMG_STORE 0
 #endif
+#ifndef ST_RAM_MINBLOCKS
+#define ST_RAM_MINBLOCKS 1
+#endif
 #ifndef ST_IMG_MINBLOCKS
 #define ST_IMG_MINBLOCKS 1
 #endif
@@ -445,7 +448,7 @@ __device__ __forceinline__ ColSlot make_col_slot(int k, const Params &p)
 template <int OBS> struct Wpc { static constexpr int value = OBS == 0 ? kRamWarpsPerCta : kWarpsPerCta; };
 
 template <int RPL, int OBS, int MODE, typename RowT>
-__global__ void __launch_bounds__(32 * Wpc<OBS>::value, OBS == 0 ? 1 : ST_IMG_MINBLOCKS) st_main_kernel(const __grid_constant__ Params p)
+__global__ void __launch_bounds__(32 * Wpc<OBS>::value, OBS == 0 ? ST_RAM_MINBLOCKS : ST_IMG_MINBLOCKS) st_main_kernel(const __grid_constant__ Params p)
 {
     constexpr int WPC = Wpc<OBS>::value;
     __shared__ __align__(16) uint32_t s_disp[WPC][32 * RPL];

@@ -163,11 +163,11 @@ class TetrisEnv(_Base):
         self.engine = EngineView(self)
 
     def _get_info(self):
-        a = self._info_buf[0]
+        """engine.get_info() (tetris_env.py:232-241) of the current device state."""
         s = self.engine._scalars()
         return {"time": int(s[5]), "current_piece": shape_names[s[0]] if s[0] < 7 else None, "score": int(s[6]),
                 "lines_cleared": int(s[7]), "holes": int(s[8]), "deaths": int(s[10]),
-                "statistics": {n: int(s[11 + i]) for i, n in enumerate(shape_names)}} if a is not None else {}
+                "statistics": {n: int(s[11 + i]) for i, n in enumerate(shape_names)}}
 
     def step(self, action):
         if isinstance(action, (bool, np.bool_)) or int(action) != action or not 0 <= int(action) <= 6:

@@ -35,6 +35,12 @@ namespace st {
 #ifndef ST_IMG_ORDER
 #define ST_IMG_ORDER 0
 #endif
+#ifndef ST_IMG_BULK
+#define ST_IMG_BULK 1
+#endif
+#ifndef ST_IMG_BULK_PASSES
+#define ST_IMG_BULK_PASSES 2
+#endif
 
 constexpr int kImgUnroll = ST_IMG_UNROLL;  // image-row loop unroll (tuning knob)
 constexpr unsigned FULL = 0xffffffffu;
@@ -454,6 +460,11 @@ __global__ void __launch_bounds__(32 * Wpc<OBS>::value, OBS == 0 ? ST_RAM_MINBLO
     __shared__ __align__(16) uint32_t s_disp[WPC][32 * RPL];
     __shared__ signed char s_rowy[OBS == 0 ? 1 : kImage];
     __shared__ unsigned char s_active[WPC];
+    // rgb: the CTA's output leaves through TMA bulk stores from a 3-deep ring of shared-memory chunks (measured
+    // +5 % over direct 16-byte stores); grayscale and ram keep direct stores (bulk stores measured 8 % slower there)
+    constexpr bool kBulk = OBS == 2 && ST_IMG_BULK != 0;
+    constexpr int kBulkPasses = ST_IMG_BULK_PASSES;
+    __shared__ __align__(128) float4 s_bulk[kBulk ? 3 : 1][kBulk ? kBulkPasses * 252 : 1];
 
     // Programmatic dependent launch: let the next step's grid start its prologue while this one runs ...
     asm volatile("griddepcontrol.launch_dependents;");
@@ -570,7 +581,50 @@ __global__ void __launch_bounds__(32 * Wpc<OBS>::value, OBS == 0 ? ST_RAM_MINBLO
         } else {
             if (lane == 0) s_active[warp] = selected && obs_p;
             __syncthreads();
-            if (threadIdx.x < KPR * NG) {
+            // TMA bulk-store path: the CTA's 8 images are one contiguous region; it is produced in chunks of
+            // kBulkPasses x 252 float4 in shared memory (3 buffers) and each chunk leaves with one
+            // cp.async.bulk.global.shared::cta issued by thread 0.  Needs all 8 envs active (a chunk straddles
+            // images); the tail CTA and masked resets take the direct-store path below.
+            bool all_active = kBulk;
+#pragma unroll
+            for (int w = 0; w < WPC; ++w) all_active = all_active && s_active[w];
+            if (kBulk && all_active) {
+                constexpr int kPassF4 = KPR * NG;                         // 252 float4 per pass
+                constexpr int kChunkF4 = kBulkPasses * kPassF4;
+                constexpr int kChunks = (WPC * kImage / NG) / kBulkPasses;  // passes per CTA / passes per chunk
+                float4 *gdst = reinterpret_cast<float4 *>(obs_p);
+                for (int c = 0; c < kChunks; ++c) {
+                    float4 *buf = s_bulk[c % 3];
+                    if (threadIdx.x < kPassF4) {
+#pragma unroll
+                        for (int q = 0; q < kBulkPasses; ++q) {
+                            const int rowg = slot_g + NG * (c * kBulkPasses + q);  // row index over the 8 images
+                            const int w = rowg / kImage, rho = rowg - w * kImage;
+                            const int code = s_rowy[rho];
+                            const uint32_t b = code >= 0 ? s_disp[w][code] : 0u;
+                            float4 v;
+                            v.x = (b & cs.mk[0]) ? cs.hi[0] : cs.lo[0];
+                            v.y = (b & cs.mk[1]) ? cs.hi[1] : cs.lo[1];
+                            v.z = (b & cs.mk[2]) ? cs.hi[2] : cs.lo[2];
+                            v.w = (b & cs.mk[3]) ? cs.hi[3] : cs.lo[3];
+                            if (code == -2) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                            buf[q * kPassF4 + threadIdx.x] = v;
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    }
+                    __syncthreads();
+                    if (threadIdx.x == 0) {
+                        const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(buf);
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst + (size_t)c * kChunkF4),
+                                     "r"(saddr), "r"((uint32_t)(kChunkF4 * sizeof(float4)))
+                                     : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // chunk c-1 has left its buffer
+                    }
+                }
+                if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncthreads();
+            } else if (threadIdx.x < KPR * NG) {
                 float4 *base = reinterpret_cast<float4 *>(obs_p) + slot_k;
 #if ST_IMG_ORDER == 1
                 // Board-row major: every board row y becomes `bs` identical image rows plus `gap` grid rows, so the

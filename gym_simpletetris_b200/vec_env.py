@@ -214,6 +214,19 @@ class VecEnv:
                                          s.data_ptr() if s is not None else None, self.num_envs, self._stream()),
                     "st_set_state")
 
+    # ---- checkpoint / resume: the whole simulator state is one tensor of env records + four counters ----
+    def state_dict(self):
+        return {"state": self.state.clone(), "stats": self.stats.clone(), "seed": self.seed,
+                "env_id_base": self.env_id_base, "num_envs": self.num_envs, "stride": self.state_stride}
+
+    def load_state_dict(self, sd):
+        if sd["num_envs"] != self.num_envs or sd["stride"] != self.state_stride:
+            raise ValueError("state_dict is for a different batch size or board geometry")
+        if sd["seed"] != self.seed or sd["env_id_base"] != self.env_id_base:
+            raise ValueError("state_dict was saved with a different seed / env_id_base: piece streams would differ")
+        self.state.copy_(sd["state"])
+        self.stats.copy_(sd["stats"])
+
     def poll_errors(self) -> int:
         """Sticky ST_ERR_* bits raised by the kernels since the last poll (synchronises)."""
         e = int(self.err.item())

@@ -422,3 +422,24 @@ def test_piece_stream_follows_reference_weighting(st):
     expect = np.array([5, 6, 6, 6, 6, 6, 6]) / 41 * m
     chi2 = float(((second - expect) ** 2 / expect).sum())
     assert chi2 < 22.46, (chi2, second, expect)
+
+
+def test_checkpoint_resume(st):
+    kw = dict(width=6, height=12, reward_step=True, lock_delay=1)
+    n = 300
+    rs = np.random.RandomState(4)
+    acts = torch.from_numpy(rs.randint(0, 7, (80, n)).astype(np.uint8)).cuda()
+    env = st.VecEnv(n, device="cuda:0", seed=21, **kw)
+    env.reset()
+    for t in range(30):
+        env.step(acts[t])
+    sd = env.state_dict()
+    a = [tuple(x.clone() for x in env.step(acts[t])[:3]) for t in range(30, 80)]
+    other = st.VecEnv(n, device="cuda:0", seed=21, **kw)
+    other.load_state_dict(sd)
+    for t in range(30, 80):
+        obs, r, d, _ = other.step(acts[t])
+        assert torch.equal(obs, a[t - 30][0]) and torch.equal(r, a[t - 30][1]) and torch.equal(d, a[t - 30][2])
+    assert other.episode_stats(reduce=False) == env.episode_stats(reduce=False)
+    with pytest.raises(ValueError):
+        st.VecEnv(n, device="cuda:0", seed=22, **kw).load_state_dict(sd)

@@ -404,12 +404,13 @@ static cudaError_t launch_tpe_t(const Params &p, cudaStream_t stream)
 
 // Measured on B200 (tools/ram_path_sweep.py, us per step; 10x20 / 20 wide x 40 high boards):
 //   n        warp    8/warp  16/warp  32/warp   |   warp    8/warp  16/warp  32/warp
-//   16384    14.8    15.1    15.9     15.3      |   19.0    27.8    35.5     37.2
-//   32768    24.9    16.2    19.4     22.2      |   33.7    31.5    46.1     57.1
-//   65536    45.6    22.8    20.8     27.7      |   62.4    49.1    58.1     73.0
-//   262144   168.9   69.7    55.8     54.7      |  234.0   170.2   182.1    195.2
-//   1048576  661.5   255.7   185.0    247.0     |  919.6   655.3   706.4    739.7
-static long long tpe_min_envs(const Params &p) { return p.H <= 31 ? 16384 : 32768; }
+//   8192     8.2     12.5    11.9     11.2      |   10.7    22.3    20.9     21.3
+//   16384    12.0    15.0    15.6     15.3      |   16.6    27.9    35.7     37.5
+//   32768    19.6    16.2    19.5     21.7      |   28.0    31.9    46.2     56.0
+//   65536    34.8    22.6    20.5     27.7      |   50.8    49.1    59.2     73.4
+//   262144   125.5   69.3    55.6     54.0      |  187.4   169.8   181.5    197.0
+//   1048576  487.5   253.6   186.4    246.5     |  733.1   652.9   703.2    738.4
+static long long tpe_min_envs(const Params &p) { return p.H <= 31 ? 24576 : 65536; }
 static int tpe_default_epw(const Params &p) { return (p.H <= 31 && p.n >= 49152) ? 16 : 8; }
 
 // Thread-per-env path: single-step ram launches with H % 4 == 0 (16-byte observation stores).

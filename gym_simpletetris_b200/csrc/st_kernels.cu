@@ -496,6 +496,10 @@ __global__ void __launch_bounds__(32 * Wpc<OBS>::value, OBS == 0 ? ST_RAM_MINBLO
     // ... and do not touch global memory before the previous grid in the stream has completed and flushed.
     asm volatile("griddepcontrol.wait;" ::: "memory");
     bool selected = valid;
+    // The action byte is the second cold miss of a step; issue its load first (asm volatile keeps it here) so that it
+    // overlaps the state loads instead of queueing behind the first shuffle that consumes them.
+    unsigned int action_u = 6u;
+    if (MODE == MODE_STEP && valid) asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(action_u) : "l"(p.actions + e));
     if (MODE == MODE_RESET && valid && p.mask && p.mask[e] == 0) selected = false;
     unsigned char *rec = p.state + (size_t)(valid ? e : 0) * (unsigned)p.stride;
     int *rec_w = reinterpret_cast<int *>(rec);
@@ -522,8 +526,7 @@ __global__ void __launch_bounds__(32 * Wpc<OBS>::value, OBS == 0 ? ST_RAM_MINBLO
     uint8_t *done_p = MODE == MODE_STEP ? p.done + e : nullptr;
     int32_t *info_p = (MODE == MODE_STEP && p.info) ? p.info + (size_t)e * kStateWords + lane : nullptr;
     float *obs_p = p.obs ? p.obs + (size_t)(OBS == 0 ? e : (int)blockIdx.x * WPC) * (unsigned)p.obs_elems : nullptr;
-    int action = 6;
-    if (MODE == MODE_STEP && selected) action = *act_p;  // issued together with the state loads
+    int action = (int)action_u;
     if (selected) pc = unpack_piece(get(sw, 0));
 #pragma unroll
     for (int k = 0; k < RPL; ++k) { row_in[k] = row[k]; disp[k] = row[k]; }

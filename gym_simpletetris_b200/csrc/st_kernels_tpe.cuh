@@ -259,6 +259,11 @@ __global__ void __launch_bounds__(32 * kTpeWarps) st_step_tpe_kernel(const __gri
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (nvalid == 0) return;
 
+    // the action bytes are issued first so that their miss overlaps the record copy
+    const int e = (int)e0 + lane;
+    unsigned int action_u = 6u;
+    if (lane < nvalid) asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(action_u) : "l"(p.actions + e));
+
     // 1. records HBM -> smem
     uint32_t *g_rec = reinterpret_cast<uint32_t *>(p.state + e0 * (long long)p.stride);
     const int nwords = nvalid * SW;
@@ -276,9 +281,8 @@ __global__ void __launch_bounds__(32 * kTpeWarps) st_step_tpe_kernel(const __gri
 
     // 2. engine, one env per lane
     const TpeRec<RowT, ROWS16> rec = {recs + lane * pitch};
-    const int e = (int)e0 + lane;
     int reward = 0, done = 0, errbits = 0;
-    if (lane < nvalid) tpe_engine_step(rec, (int)p.actions[e], p, e, walls, s_tab, reward, done, errbits);
+    if (lane < nvalid) tpe_engine_step(rec, (int)action_u, p, e, walls, s_tab, reward, done, errbits);
     __syncwarp();
 
     // 3. info (pre-reset), reward, done; then auto-reset or piece overlay

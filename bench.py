@@ -50,8 +50,8 @@ WORKLOADS = {
 # `ncu --set full` captures summarised in profiles/r1_<workload>_step_kernel_ncu_full.txt.  ncu flushes caches
 # before the single replayed launch and stops at kernel end, so writes still sitting in the 126 MB L2 are not
 # counted: the small ram workloads read their state from DRAM but their observations stay in L2.
-NCU_TRAFFIC_BYTES = {"C2": 440576 + 0, "C3": 6670592 + 7860736, "C4": 27191808 + 7383049000,
-                     "C5a": 19105536 + 11061010000, "C5b": 14545920 + 171609344}
+NCU_TRAFFIC_BYTES = {"C2": 440576 + 0, "C3": 6670592 + 8063232, "C4": 27588352 + 7380657000,
+                     "C5a": 19003904 + 11060443000, "C5b": 14771712 + 172492544}
 HEADLINE = "C2"
 L2_BYTES = 126 << 20
 

@@ -13,7 +13,9 @@ def pytest_configure(config):
 
 
 @pytest.fixture(scope="session", autouse=True)
-def _build_oracle():
-    from oracle.oracle import build_oracle
+def _build_everything():
+    """Build what the tests load if it is not there yet (a fresh clone has no .so files): the CUDA library with
+    nvcc (cross-compiles without a GPU) and the C oracle with gcc."""
+    import __graft_entry__ as entry
 
-    build_oracle()
+    entry.build()

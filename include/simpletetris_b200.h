@@ -119,7 +119,8 @@ ST_API int st_reset(const StConfig *cfg, void *state, const uint8_t *mask, float
 ST_API int st_step(const StConfig *cfg, void *state, const uint8_t *actions, float *obs, float *reward,
             uint8_t *done, int32_t *info, const StAux *aux, int64_t n, void *stream);
 
-/* T consecutive steps in one launch (state stays in registers between steps).  actions [T][n];
+/* T consecutive TetrisEnv.step calls (ref:397-403) in one launch: the caller loop of README.md:43-51 moved on the
+ * device (state stays in registers between steps).  actions [T][n];
  * reward/done [T][n]; obs and info advance by obs_t_stride / info_t_stride ELEMENTS per step (0 = every
  * step overwrites the same [n][...] buffer, n*elems = a rollout buffer). */
 ST_API int st_step_many(const StConfig *cfg, void *state, const uint8_t *actions, int32_t T, float *obs,
@@ -136,7 +137,9 @@ ST_API int st_render(const StConfig *cfg, const void *state, int32_t draw_piece,
                      int64_t n, void *stream);
 
 /* ---- state injection / inspection (tests, checkpoints) -------------------------- */
-/* boards [n][W][H] uint8 (ref board[x,y]);  scalars [n][ST_UNPACKED_WORDS] int32: piece id (7 = none),
+/* What a test of the reference does by reading / assigning engine.board (ref:140), engine.shape / anchor /
+ * shape_name (ref:170-172,196-200), the counters of ref:165-169,173, _lock_delay (ref:176) and shape_counts (ref:181).
+ * boards [n][W][H] uint8 (ref board[x,y]);  scalars [n][ST_UNPACKED_WORDS] int32: piece id (7 = none),
  * rotation (number of rotate_left applications, ref:22-26), anchor x, anchor y, lock-delay counter, time,
  * score, lines_cleared, holes, piece_height, deaths, shape_counts[7].  Either pointer may be NULL. */
 ST_API int st_get_state(const StConfig *cfg, const void *state, uint8_t *boards, int32_t *scalars, int64_t n, void *stream);
@@ -144,13 +147,16 @@ ST_API int st_set_state(const StConfig *cfg, void *state, const uint8_t *boards,
 
 /* ---- host-buffer handle (owns its device memory; synchronous) -------------------- */
 typedef struct StHostEnv StHostEnv;
-/* Allocates state/obs/... for n envs on cfg->device and runs st_init.  NULL on failure. */
+/* TetrisEnv.__init__ (ref:343-392) for n envs: allocates state/obs/... on cfg->device and runs st_init.  NULL on
+ * failure (st_last_error() says why). */
 ST_API StHostEnv *st_host_create(const StConfig *cfg, int64_t n);
 ST_API void st_host_destroy(StHostEnv *h);
-/* queue: host [n][queue_len] or NULL to go back to the Philox stream. */
+/* Replaces engine._choose_shape (ref:183-191) by a fixed sequence: queue = host [n][queue_len], or NULL to go back
+ * to the Philox stream. */
 ST_API int st_host_set_piece_queue(StHostEnv *h, const uint8_t *queue, int32_t queue_len);
-/* All pointers are HOST memory (pinned memory makes the copies asynchronous until the final sync);
- * obs/info/mask may be NULL.  Copies actions in, launches, copies results out, synchronises. */
+/* TetrisEnv.reset (ref:405-411) / TetrisEnv.step (ref:397-403) / engine.render() through _observation
+ * (ref:317-321, 413-433) with HOST buffers, as a NumPy caller of the reference sees them.  obs/info/mask may be
+ * NULL.  Copies (or maps, see st_host_set_zero_copy) the inputs in, launches, brings the results out, synchronises. */
 ST_API int st_host_reset(StHostEnv *h, const uint8_t *mask, float *obs);
 ST_API int st_host_step(StHostEnv *h, const uint8_t *actions, float *obs, float *reward, uint8_t *done, int32_t *info);
 ST_API int st_host_observe(StHostEnv *h, int32_t draw_piece, float *obs);

@@ -99,11 +99,21 @@ def run_vec(st, n, acts, seed=0, env_id_base=0, per_step_obs=False, **kw):
                 info=np.stack(inf), obs_t=obs_t, env=env)
 
 
-@pytest.mark.parametrize("name", list(CASES))
+# extra geometries checked against the oracle only: wide boards (64-bit row registers) whose height is divisible by
+# 4, so that the thread-per-env kernel's 64-bit instantiation is exercised too
+EXTRA_CASES = {
+    "w28h24_wide": dict(width=28, height=24, penalise_holes=True, reward_step=True),
+    "w26h40_wide_tall": dict(width=26, height=40, lock_delay=2, step_reset=True, penalise_height_increase=True),
+    "w25h8_wide_low": dict(width=25, height=8, advanced_clears=True),
+    "w5h60_narrow_tall": dict(width=5, height=60, high_scoring=True, penalise_holes_increase=True),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES) + list(EXTRA_CASES))
 def test_vecenv_matches_oracle(st, name):
     from oracle.oracle import rollout
 
-    kw = CASES[name]
+    kw = CASES[name] if name in CASES else EXTRA_CASES[name]
     image = kw.get("obs_type", "ram") != "ram"
     n, T = (37, 150) if image else (261, 400)  # ragged: not a multiple of the 8 envs per CTA
     acts = np.random.RandomState(11).randint(0, 7, (T, n)).astype(np.uint8)

@@ -286,8 +286,14 @@ def time_e2e(name, steps, warmup, rank, world, dist, zero_copy=None):
     info = torch.empty((n, native.ST_INFO_WORDS), dtype=torch.int32).pin_memory()
     acts = torch.from_numpy(np.random.RandomState(7 + rank).randint(0, 7, (warmup + steps, n)).astype(np.uint8)).pin_memory()
     native.check(L.st_host_reset(h, None, obs.data_ptr()), "st_host_reset")
-    step = lambda t: native.check(L.st_host_step(h, acts[t].data_ptr(), obs.data_ptr(), reward.data_ptr(),
-                                                 done.data_ptr(), info.data_ptr()), "st_host_step")
+    a_ptr = [acts[t].data_ptr() for t in range(warmup + steps)]  # row pointers of the pinned action matrix
+    o_ptr, r_ptr, d_ptr, i_ptr = obs.data_ptr(), reward.data_ptr(), done.data_ptr(), info.data_ptr()
+    host_step = L.st_host_step
+
+    def step(t):
+        rc = host_step(h, a_ptr[t], o_ptr, r_ptr, d_ptr, i_ptr)
+        if rc:
+            native.check(rc, "st_host_step")
     for t in range(warmup):
         step(t)
     if world > 1:

@@ -333,8 +333,22 @@ __global__ void __launch_bounds__(32 * kTpeWarps) st_step_tpe_kernel(const __gri
     }
     __syncwarp();
 
-    // 4. observations: float32 [W][H] per env (ref:421-424, 400); launch_main only takes this path if H % 4 == 0
-    if (p.obs) {
+    // 4. observations: float32 [W][H] per env (ref:421-424, 400); 16-byte stores when H % 4 == 0, else 4-byte ones
+    if (p.obs && (H & 3) != 0) {
+        const int nel = W * H;
+        float *o = p.obs + e0 * (long long)p.obs_elems;
+        for (int i0 = 0; i0 < nel; i0 += 32) {
+            const int i = i0 + lane;
+            const int x = (int)(((uint32_t)i * p.inv_h20) >> 20);
+            const int yy = i - x * H;
+            if (i < nel) {
+                for (int r = 0; r < nvalid; ++r) {
+                    const TpeRec<RowT, ROWS16> rr = {recs + r * pitch};
+                    o[r * nel + i] = ((rr.raw(yy) >> x) & 1u) ? 1.0f : 0.0f;
+                }
+            }
+        }
+    } else if (p.obs) {
         const int hq = H >> 2, nq = W * hq;
         float4 *o4 = reinterpret_cast<float4 *>(p.obs + e0 * (long long)p.obs_elems);
         for (int q0 = 0; q0 < nq; q0 += 32) {
@@ -417,10 +431,10 @@ static cudaError_t launch_tpe_t(const Params &p, cudaStream_t stream)
 static long long tpe_min_envs(const Params &p) { return p.H <= 31 ? 24576 : 65536; }
 static int tpe_default_epw(const Params &p) { return (p.H <= 31 && p.n >= 49152) ? 16 : 8; }
 
-// Thread-per-env path: single-step ram launches with H % 4 == 0 (16-byte observation stores).
+// Thread-per-env path: single-step ram launches.
 static bool tpe_eligible(const Params &p, int obs_type)
 {
-    return obs_type == 0 && p.mode == MODE_STEP && p.T == 1 && (p.H & 3) == 0 && p.n > 0;
+    return obs_type == 0 && p.mode == MODE_STEP && p.T == 1 && p.n > 0;
 }
 
 static cudaError_t launch_tpe(const Params &p0, cudaStream_t stream)

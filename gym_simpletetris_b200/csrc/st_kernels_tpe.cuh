@@ -279,15 +279,20 @@ __global__ void __launch_bounds__(32 * kTpeWarps) st_step_tpe_kernel(const __gri
     }
     __syncwarp();
 
-    // 2. engine, one env per lane
     const TpeRec<RowT, ROWS16> rec = {recs + lane * pitch};
-    int reward = 0, done = 0, errbits = 0;
+    int errbits = 0;
+    const size_t n_envs = (size_t)p.n;
+    for (int t = 0; t < p.T; ++t) {  // st_step_many: the records stay in shared memory between steps
+    // 2. engine, one env per lane
+    int reward = 0, done = 0;
     if (lane < nvalid) tpe_engine_step(rec, (int)action_u, p, e, walls, s_tab, reward, done, errbits);
+    if (t + 1 < p.T && lane < nvalid)  // next step's action, in flight during the cooperative phases
+        asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(action_u) : "l"(p.actions + (size_t)(t + 1) * n_envs + e));
     __syncwarp();
 
     // 3. info (pre-reset), reward, done; then auto-reset or piece overlay
     if (p.info) {
-        int32_t *g_info = p.info + e0 * kStateWords;
+        int32_t *g_info = p.info + (long long)t * p.info_t_stride + e0 * kStateWords;
         for (int j = lane; j < nvalid * kStateWords; j += 32) {
             const int r = (j * 4370) >> 16;  // j / 15 for j < 480
             const int c = j - r * kStateWords;
@@ -296,8 +301,8 @@ __global__ void __launch_bounds__(32 * kTpeWarps) st_step_tpe_kernel(const __gri
         }
     }
     if (lane < nvalid) {
-        p.reward[e] = (float)reward;
-        p.done[e] = (unsigned char)done;
+        p.reward[(size_t)t * n_envs + e] = (float)reward;
+        p.done[(size_t)t * n_envs + e] = (unsigned char)done;
         if (done && p.stats) {
             atomicAdd(p.stats, 1ull);
             atomicAdd(p.stats + 1, (unsigned long long)(long long)(int)rec.w[2]);
@@ -336,7 +341,7 @@ __global__ void __launch_bounds__(32 * kTpeWarps) st_step_tpe_kernel(const __gri
     // 4. observations: float32 [W][H] per env (ref:421-424, 400); 16-byte stores when H % 4 == 0, else 4-byte ones
     if (p.obs && (H & 3) != 0) {
         const int nel = W * H;
-        float *o = p.obs + e0 * (long long)p.obs_elems;
+        float *o = p.obs + (long long)t * p.obs_t_stride + e0 * (long long)p.obs_elems;
         for (int i0 = 0; i0 < nel; i0 += 32) {
             const int i = i0 + lane;
             const int x = (int)(((uint32_t)i * p.inv_h20) >> 20);
@@ -350,7 +355,7 @@ __global__ void __launch_bounds__(32 * kTpeWarps) st_step_tpe_kernel(const __gri
         }
     } else if (p.obs) {
         const int hq = H >> 2, nq = W * hq;
-        float4 *o4 = reinterpret_cast<float4 *>(p.obs + e0 * (long long)p.obs_elems);
+        float4 *o4 = reinterpret_cast<float4 *>(p.obs + (long long)t * p.obs_t_stride + e0 * (long long)p.obs_elems);
         for (int q0 = 0; q0 < nq; q0 += 32) {
             const int q = q0 + lane;
             const int x = (int)(((uint32_t)q * p.inv_hq20) >> 20);
@@ -378,10 +383,11 @@ __global__ void __launch_bounds__(32 * kTpeWarps) st_step_tpe_kernel(const __gri
     // 5. _set_piece(False) (ref:303), literally: the cells of the piece are cleared on the board
     if (lane < nvalid) {
 #pragma unroll
-        for (int t = 0; t < 4; ++t)
-            if (pbits[t]) rec.set_raw(ptop + t, rec.raw(ptop + t) & ~pbits[t]);
+        for (int k = 0; k < 4; ++k)
+            if (pbits[k]) rec.set_raw(ptop + k, rec.raw(ptop + k) & ~pbits[k]);
     }
     __syncwarp();
+    }  // for t
     if (pitch == SW) {
         const int nvec = nwords >> 2;
         for (int i = lane; i < nvec; i += 32) reinterpret_cast<uint4 *>(g_rec)[i] = reinterpret_cast<const uint4 *>(recs)[i];
@@ -434,7 +440,7 @@ static int tpe_default_epw(const Params &p) { return (p.H <= 31 && p.n >= 49152)
 // Thread-per-env path: single-step ram launches.
 static bool tpe_eligible(const Params &p, int obs_type)
 {
-    return obs_type == 0 && p.mode == MODE_STEP && p.T == 1 && p.n > 0;
+    return obs_type == 0 && p.mode == MODE_STEP && p.n > 0 && (p.obs_t_stride & 3) == 0;
 }
 
 static cudaError_t launch_tpe(const Params &p0, cudaStream_t stream)

@@ -1,7 +1,7 @@
 """BASELINE config C5a on ONE GPU: 2^20 envs with rgb 84x84x3 float32 observations (88.8 GB) — index arithmetic
 at full size, spot-checked against the oracle (run on the GPU box)."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 import gym_simpletetris_b200 as st

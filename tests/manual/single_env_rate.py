@@ -1,6 +1,6 @@
 """Steps/s of the single-env NumPy facade (N=1: launch-latency bound) next to the CPU oracle (run on the GPU box)."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import gym_simpletetris_b200 as st
 from oracle.oracle import OracleEnv

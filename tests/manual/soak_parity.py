@@ -1,8 +1,8 @@
 """Long randomized parity soak: VecEnv (both ram kernels, image modes) vs the C oracle on the same Philox streams.
-Not part of the test suite (minutes of CPU time); run on the GPU box:  python tools/soak_parity.py"""
+Not part of the test suite (minutes of CPU time); run on the GPU box:  python tests/manual/soak_parity.py"""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests"))
 import numpy as np
 import torch
 import gym_simpletetris_b200 as st

@@ -2,12 +2,14 @@
 
     python examples/random_rollout.py [num_envs] [obs_type]
 """
+import os
 import sys
 import time
 
 import torch
 
-import gym_simpletetris_b200 as st
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # run from a checkout
+import gym_simpletetris_b200 as st  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 obs_type = sys.argv[2] if len(sys.argv) > 2 else "ram"

@@ -18,7 +18,10 @@
 
 namespace st {
 
-constexpr int kTpeWarps = 4;
+#ifndef ST_TPE_WARPS
+#define ST_TPE_WARPS 4
+#endif
+constexpr int kTpeWarps = ST_TPE_WARPS;
 
 template <typename RowT, bool ROWS16>
 struct TpeRec {
@@ -208,6 +211,9 @@ __device__ __forceinline__ void tpe_engine_step(const TpeRec<RowT, ROWS16> &rec,
     int y = pc.y;
     int ld = (int)rec.w[1];
     bool grounded;
+#ifdef ST_TPE_WHATIF_NODROP  // timing experiments only
+    if (action == 2) action = 6;
+#endif
     if (action == 2) {  // hard_drop (ref:54-59): first colliding anchor below, four candidates per window
         uint32_t c4 = cm >> 1;  // anchors y+1 .. y+3 are already known
         int ya = y + 1;
@@ -232,7 +238,9 @@ __device__ __forceinline__ void tpe_engine_step(const TpeRec<RowT, ROWS16> &rec,
     if (grounded) {
         ld += 1;
         if (ld >= p.lock_mod) ld %= p.lock_mod;
+#ifndef ST_TPE_WHATIF_NOLOCK  // timing experiments only
         if (ld == 0) tpe_lock(rec, pc, pr, p, e, reward, done, errbits);
+#endif
     }
     rec.w[1] = (uint32_t)ld;
     rec.w[0] = (uint32_t)pack_piece(pc);

@@ -52,6 +52,15 @@ WORKLOADS = {
 # counted: the small ram workloads read their state from DRAM but their observations stay in L2.
 NCU_TRAFFIC_BYTES = {"C2": 440576 + 0, "C3": 6670592 + 8063232, "C4": 27588352 + 7380657000,
                      "C5a": 19003904 + 11060443000, "C5b": 14771712 + 172492544}
+# uint8-observation extension (same values, a quarter of the observation bytes): reported separately, with its own
+# algorithmic bytes, and only when asked for with --modes ...,C4_u8,C5a_u8 or --modes all+u8
+U8_WORKLOADS = {
+    "C4_u8": dict(n=262144, kw=dict(obs_type="grayscale", extend_dims=True, high_scoring=True, obs_dtype="uint8"),
+                  desc="C4 with uint8 observations (extension, not the float32 parity mode): 262144 envs/GPU, grayscale"),
+    "C5a_u8": dict(n=131072, kw=dict(obs_type="rgb", obs_dtype="uint8"),
+                   desc="C5a with uint8 observations (extension, not the float32 parity mode): 131072 envs/GPU, rgb"),
+}
+WORKLOADS.update(U8_WORKLOADS)
 HEADLINE = "C2"
 L2_BYTES = 126 << 20
 
@@ -60,7 +69,8 @@ def algorithmic_bytes(kw):
     """obs_bytes (float32) + 2 * state_bytes + 6 (action 1, reward 4, done 1)."""
     W, H = kw.get("width", 10), kw.get("height", 20)
     ot = kw.get("obs_type", "ram")
-    obs = 4 * (W * H if ot == "ram" else 84 * 84 * (3 if ot == "rgb" else 1))
+    esz = 1 if kw.get("obs_dtype") == "uint8" else 4
+    obs = esz * (W * H if ot == "ram" else 84 * 84 * (3 if ot == "rgb" else 1))
     state = 60 + H * (2 if W <= 16 else 4)
     return obs + 2 * state + 6
 
@@ -152,9 +162,11 @@ def time_workload(name, steps, warmup, rank, world, dist, burn_in=200):
 
     import gym_simpletetris_b200 as st
     wl = WORKLOADS[name]
-    n, kw = wl["n"], wl["kw"]
+    n, kw = wl["n"], dict(wl["kw"])
     dev = torch.device("cuda", torch.cuda.current_device())
     B = algorithmic_bytes(kw)
+    if kw.get("obs_dtype") == "uint8":
+        kw["obs_dtype"] = torch.uint8
     R = max(1, -(-int(2.5 * L2_BYTES) // (B * n)))
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
     image = kw.get("obs_type", "ram") != "ram"
@@ -417,11 +429,13 @@ def main():
     head = time_workload(args.workload, args.steps, args.warmup, rank, world, dist)
     e2e = None if args.no_e2e else time_e2e(args.workload, min(args.steps, 200), args.warmup, rank, world, dist)
     modes = {}
-    names = [] if args.modes == "none" else ([k for k in WORKLOADS if k != args.workload] if args.modes == "all"
-                                              else args.modes.split(","))
+    base = [k for k in WORKLOADS if k != args.workload and k not in U8_WORKLOADS]
+    names = [] if args.modes == "none" else (base if args.modes == "all" else
+                                              base + list(U8_WORKLOADS) if args.modes == "all+u8" else args.modes.split(","))
     for nm in names:
         r = time_workload(nm, args.mode_steps, max(3, min(args.warmup, 5)), rank, world, dist)
-        r["e2e"] = time_e2e(nm, 5, 3, rank, world, dist) if WORKLOADS[nm]["n"] * algorithmic_bytes(WORKLOADS[nm]["kw"]) < (2 << 30) else None
+        small = WORKLOADS[nm]["n"] * algorithmic_bytes(WORKLOADS[nm]["kw"]) < (2 << 30) and nm not in U8_WORKLOADS
+        r["e2e"] = time_e2e(nm, 5, 3, rank, world, dist) if small else None
         modes[nm] = r
     fill_gbs = write_only_ceiling_gbs() if rank == 0 else None
     clocks = sampler.stop()

@@ -56,6 +56,7 @@ int make_params(const StConfig *c, const StAux *aux, int64_t n, st::Params *out)
     p.seed_hi = (uint32_t)(c->seed >> 32);
     p.env_id_base = c->env_id_base;
     p.obs_elems = (int)st_obs_elems(c);
+    p.obs_u8 = c->obs_u8 != 0;
     // convert_grayscale geometry at size 84 (ref:84-94); the transposed array is (H, W)
     const int size = st::kImage;
     const int limiting = c->width > c->height ? c->width : c->height;
@@ -123,7 +124,7 @@ int st_init(const StConfig *cfg, void *state, int64_t n, void *stream)
     return e == cudaSuccess ? 0 : fail_cuda(e, "st_init");
 }
 
-int st_reset(const StConfig *cfg, void *state, const uint8_t *mask, float *obs, const StAux *aux, int64_t n,
+int st_reset(const StConfig *cfg, void *state, const uint8_t *mask, void *obs, const StAux *aux, int64_t n,
              void *stream)
 {
     st::Params p;
@@ -138,7 +139,7 @@ int st_reset(const StConfig *cfg, void *state, const uint8_t *mask, float *obs, 
     return e == cudaSuccess ? 0 : fail_cuda(e, "st_reset");
 }
 
-int st_step_many(const StConfig *cfg, void *state, const uint8_t *actions, int32_t T, float *obs,
+int st_step_many(const StConfig *cfg, void *state, const uint8_t *actions, int32_t T, void *obs,
                  int64_t obs_t_stride, float *reward, uint8_t *done, int32_t *info, int64_t info_t_stride,
                  const StAux *aux, int64_t n, void *stream)
 {
@@ -162,13 +163,13 @@ int st_step_many(const StConfig *cfg, void *state, const uint8_t *actions, int32
     return e == cudaSuccess ? 0 : fail_cuda(e, "st_step");
 }
 
-int st_step(const StConfig *cfg, void *state, const uint8_t *actions, float *obs, float *reward, uint8_t *done,
+int st_step(const StConfig *cfg, void *state, const uint8_t *actions, void *obs, float *reward, uint8_t *done,
             int32_t *info, const StAux *aux, int64_t n, void *stream)
 {
     return st_step_many(cfg, state, actions, 1, obs, 0, reward, done, info, 0, aux, n, stream);
 }
 
-int st_observe(const StConfig *cfg, const void *state, int32_t draw_piece, float *obs, int64_t n, void *stream)
+int st_observe(const StConfig *cfg, const void *state, int32_t draw_piece, void *obs, int64_t n, void *stream)
 {
     st::Params p;
     if (int rc = make_params(cfg, nullptr, n, &p)) return rc;
@@ -227,10 +228,11 @@ struct StHostEnv {
     StConfig cfg;
     int64_t n;
     int64_t obs_elems;
+    size_t obs_esz;  // 4 (float32, reference dtype) or 1 (uint8 mode)
     cudaStream_t stream;
     void *state;
     uint8_t *actions;
-    float *obs;
+    void *obs;
     float *reward;
     uint8_t *done;
     int32_t *info;
@@ -323,13 +325,14 @@ StHostEnv *st_host_create(const StConfig *cfg, int64_t n)
     h->cfg = *cfg;
     h->n = n;
     h->obs_elems = st_obs_elems(cfg);
+    h->obs_esz = cfg->obs_u8 ? 1 : 4;
     // small batches: the kernel writes straight into page-locked caller buffers (saves four copy launches);
     // large ones: the copy engine moves the observation block at link rate
-    h->zero_copy = (n * (h->obs_elems * 4 + 65) <= (8ll << 20)) ? (ST_ZC_ACTIONS | ST_ZC_SMALL | ST_ZC_OBS) : 0;
+    h->zero_copy = (n * (h->obs_elems * (int64_t)h->obs_esz + 65) <= (8ll << 20)) ? (ST_ZC_ACTIONS | ST_ZC_SMALL | ST_ZC_OBS) : 0;
     bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaMalloc(&h->state, (size_t)(st_state_stride(cfg) * n)) == cudaSuccess;
     ok = ok && cudaMalloc((void **)&h->actions, (size_t)n) == cudaSuccess;
-    ok = ok && cudaMalloc((void **)&h->obs, (size_t)(h->obs_elems * n) * sizeof(float)) == cudaSuccess;
+    ok = ok && cudaMalloc((void **)&h->obs, (size_t)(h->obs_elems * n) * h->obs_esz) == cudaSuccess;
     ok = ok && cudaMalloc((void **)&h->reward, (size_t)n * sizeof(float)) == cudaSuccess;
     ok = ok && cudaMalloc((void **)&h->done, (size_t)n) == cudaSuccess;
     ok = ok && cudaMalloc((void **)&h->info, (size_t)n * ST_INFO_WORDS * sizeof(int32_t)) == cudaSuccess;
@@ -377,7 +380,7 @@ int st_host_set_piece_queue(StHostEnv *h, const uint8_t *queue, int32_t queue_le
     return 0;
 }
 
-int st_host_reset(StHostEnv *h, const uint8_t *mask, float *obs)
+int st_host_reset(StHostEnv *h, const uint8_t *mask, void *obs)
 {
     if (!h) return fail(ST_E_INVALID, "NULL handle%s");
     if (int rc = use_device(&h->cfg)) return rc;
@@ -385,13 +388,13 @@ int st_host_reset(StHostEnv *h, const uint8_t *mask, float *obs)
     StAux aux = host_aux(h);
     if (int rc = st_reset(&h->cfg, h->state, mask ? h->mask : nullptr, h->obs, &aux, h->n, h->stream)) return rc;
     if (obs)
-        HCHECK(cudaMemcpyAsync(obs, h->obs, (size_t)(h->obs_elems * h->n) * sizeof(float), cudaMemcpyDeviceToHost,
+        HCHECK(cudaMemcpyAsync(obs, h->obs, (size_t)(h->obs_elems * h->n) * h->obs_esz, cudaMemcpyDeviceToHost,
                                h->stream), "D2H obs");
     HCHECK(cudaStreamSynchronize(h->stream), "st_host_reset");
     return 0;
 }
 
-int st_host_step(StHostEnv *h, const uint8_t *actions, float *obs, float *reward, uint8_t *done, int32_t *info)
+int st_host_step(StHostEnv *h, const uint8_t *actions, void *obs, float *reward, uint8_t *done, int32_t *info)
 {
     if (!h || !actions) return fail(ST_E_INVALID, "NULL handle/actions%s");
     if (int rc = use_device(&h->cfg)) return rc;
@@ -399,7 +402,7 @@ int st_host_step(StHostEnv *h, const uint8_t *actions, float *obs, float *reward
     // extra copy launches); pageable ones go through the handle's device buffers and cudaMemcpyAsync.
     const int zc = h->zero_copy;
     const uint8_t *d_act = (zc & ST_ZC_ACTIONS) ? (const uint8_t *)mapped_alias(h, 0, actions) : nullptr;
-    float *d_obs = (zc & ST_ZC_OBS) ? (float *)mapped_alias(h, 1, obs) : nullptr;
+    void *d_obs = (zc & ST_ZC_OBS) ? mapped_alias(h, 1, obs) : nullptr;
     float *d_rew = (zc & ST_ZC_SMALL) ? (float *)mapped_alias(h, 2, reward) : nullptr;
     uint8_t *d_done = (zc & ST_ZC_SMALL) ? (uint8_t *)mapped_alias(h, 3, done) : nullptr;
     int32_t *d_info = (zc & ST_ZC_SMALL) ? (int32_t *)mapped_alias(h, 4, info) : nullptr;
@@ -413,7 +416,7 @@ int st_host_step(StHostEnv *h, const uint8_t *actions, float *obs, float *reward
                          h->stream))
         return rc;
     if (obs && !d_obs)
-        HCHECK(cudaMemcpyAsync(obs, h->obs, (size_t)(h->obs_elems * h->n) * sizeof(float), cudaMemcpyDeviceToHost,
+        HCHECK(cudaMemcpyAsync(obs, h->obs, (size_t)(h->obs_elems * h->n) * h->obs_esz, cudaMemcpyDeviceToHost,
                                h->stream), "D2H obs");
     if (reward && !d_rew)
         HCHECK(cudaMemcpyAsync(reward, h->reward, (size_t)h->n * sizeof(float), cudaMemcpyDeviceToHost, h->stream),
@@ -426,12 +429,12 @@ int st_host_step(StHostEnv *h, const uint8_t *actions, float *obs, float *reward
     return 0;
 }
 
-int st_host_observe(StHostEnv *h, int32_t draw_piece, float *obs)
+int st_host_observe(StHostEnv *h, int32_t draw_piece, void *obs)
 {
     if (!h || !obs) return fail(ST_E_INVALID, "NULL handle/obs%s");
     if (int rc = use_device(&h->cfg)) return rc;
     if (int rc = st_observe(&h->cfg, h->state, draw_piece, h->obs, h->n, h->stream)) return rc;
-    HCHECK(cudaMemcpyAsync(obs, h->obs, (size_t)(h->obs_elems * h->n) * sizeof(float), cudaMemcpyDeviceToHost,
+    HCHECK(cudaMemcpyAsync(obs, h->obs, (size_t)(h->obs_elems * h->n) * h->obs_esz, cudaMemcpyDeviceToHost,
                            h->stream), "D2H obs");
     HCHECK(cudaStreamSynchronize(h->stream), "st_host_observe");
     return 0;

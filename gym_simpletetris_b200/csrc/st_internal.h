@@ -37,7 +37,8 @@ struct Params {
     // buffers
     unsigned char *state;
     const uint8_t *actions;
-    float *obs;
+    void *obs;       // float32 [n][obs_elems], or uint8 when obs_u8
+    int obs_u8;
     float *reward;
     uint8_t *done;
     int32_t *info;

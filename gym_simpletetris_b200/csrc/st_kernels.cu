@@ -20,9 +20,6 @@
 
 namespace st {
 
-#ifndef ST_IMG_STORE
-#define ST_IMG_STORE 0
-#endif
 #ifndef ST_FORCE_MANY
 #define ST_FORCE_MANY 0
 #endif
@@ -34,9 +31,6 @@ namespace st {
 #endif
 #ifndef ST_IMG_UNROLL
 #define ST_IMG_UNROLL 1
-#endif
-#ifndef ST_IMG_ORDER
-#define ST_IMG_ORDER 0
 #endif
 #ifndef ST_IMG_BULK
 #define ST_IMG_BULK 1
@@ -400,27 +394,40 @@ __device__ __forceinline__ void engine_step(RowT (&row)[RPL], RowT (&disp)[RPL],
 // ---------------------------------------------------------------------------------------------
 // Observation writers
 // ---------------------------------------------------------------------------------------------
+// Four consecutive observation elements: one 16-byte store in the reference's float32, or one 4-byte store in
+// the uint8 mode (same values: 0/1 for ram, 0/128/190 for images; reported separately, never as the parity mode).
+__device__ __forceinline__ void store4(void *obs, size_t idx4, const float4 &v, bool u8)
+{
+    if (u8)
+        reinterpret_cast<uchar4 *>(obs)[idx4] =
+            make_uchar4((unsigned char)v.x, (unsigned char)v.y, (unsigned char)v.z, (unsigned char)v.w);
+    else
+        reinterpret_cast<float4 *>(obs)[idx4] = v;
+}
+
 // ram (ref:421-424 + float32 cast ref:400): out[x][y] = cell (x,y); rows come from the warp's smem row.
-__device__ __forceinline__ void write_ram(const uint32_t *srow, float *out, const Params &p, int lane)
+__device__ __forceinline__ void write_ram(const uint32_t *srow, void *out, const Params &p, int lane)
 {
     const int H = p.H, W = p.W;
+    const bool u8 = p.obs_u8 != 0;
     if ((H & 3) == 0) {
         const int nq = (W * H) >> 2, hq = H >> 2;
-        float4 *o4 = reinterpret_cast<float4 *>(out);
         for (int q = lane; q < nq; q += 32) {
             const int x = (int)(((uint32_t)q * p.inv_hq20) >> 20);
             const int yq = q - x * hq;
             const uint32_t bit = 1u << x;
             const uint4 r = reinterpret_cast<const uint4 *>(srow)[yq];
-            o4[q] = make_float4((r.x & bit) ? 1.0f : 0.0f, (r.y & bit) ? 1.0f : 0.0f, (r.z & bit) ? 1.0f : 0.0f,
-                                (r.w & bit) ? 1.0f : 0.0f);
+            store4(out, q, make_float4((r.x & bit) ? 1.0f : 0.0f, (r.y & bit) ? 1.0f : 0.0f, (r.z & bit) ? 1.0f : 0.0f,
+                                       (r.w & bit) ? 1.0f : 0.0f), u8);
         }
     } else {
         const int nel = W * H;
         for (int i = lane; i < nel; i += 32) {
             const int x = (int)(((uint32_t)i * p.inv_h20) >> 20);
             const int yy = i - x * H;
-            out[i] = ((srow[yy] >> x) & 1u) ? 1.0f : 0.0f;
+            const bool on = ((srow[yy] >> x) & 1u) != 0u;
+            if (u8) reinterpret_cast<unsigned char *>(out)[i] = on ? 1 : 0;
+            else reinterpret_cast<float *>(out)[i] = on ? 1.0f : 0.0f;
         }
     }
 }
@@ -525,7 +532,10 @@ __global__ void __launch_bounds__(32 * Wpc<OBS>::value, OBS == 0 ? ST_RAM_MINBLO
     float *rew_p = MODE == MODE_STEP ? p.reward + e : nullptr;
     uint8_t *done_p = MODE == MODE_STEP ? p.done + e : nullptr;
     int32_t *info_p = (MODE == MODE_STEP && p.info) ? p.info + (size_t)e * kStateWords + lane : nullptr;
-    float *obs_p = p.obs ? p.obs + (size_t)(OBS == 0 ? e : (int)blockIdx.x * WPC) * (unsigned)p.obs_elems : nullptr;
+    const bool u8 = p.obs_u8 != 0;
+    const size_t esz = u8 ? 1 : 4;  // bytes per observation element
+    char *obs_p = p.obs ? reinterpret_cast<char *>(p.obs) + (size_t)(OBS == 0 ? e : (int)blockIdx.x * WPC) * (unsigned)p.obs_elems * esz
+                        : nullptr;
     int action = (int)action_u;
     if (selected) pc = unpack_piece(get(sw, 0));
 #pragma unroll
@@ -598,7 +608,7 @@ __global__ void __launch_bounds__(32 * Wpc<OBS>::value, OBS == 0 ? ST_RAM_MINBLO
                 constexpr int kPassF4 = KPR * NG;                         // 252 float4 per pass
                 constexpr int kChunkF4 = kBulkPasses * kPassF4;
                 constexpr int kChunks = (WPC * kImage / NG) / kBulkPasses;  // passes per CTA / passes per chunk
-                float4 *gdst = reinterpret_cast<float4 *>(obs_p);
+                const uint32_t chunk_bytes = (uint32_t)(kChunkF4 * (u8 ? sizeof(uchar4) : sizeof(float4)));
                 for (int c = 0; c < kChunks; ++c) {
                     float4 *buf = s_bulk[c % 3];
                     if (threadIdx.x < kPassF4) {
@@ -614,15 +624,15 @@ __global__ void __launch_bounds__(32 * Wpc<OBS>::value, OBS == 0 ? ST_RAM_MINBLO
                             v.z = (b & cs.mk[2]) ? cs.hi[2] : cs.lo[2];
                             v.w = (b & cs.mk[3]) ? cs.hi[3] : cs.lo[3];
                             if (code == -2) v = make_float4(0.f, 0.f, 0.f, 0.f);
-                            buf[q * kPassF4 + threadIdx.x] = v;
+                            store4(buf, q * kPassF4 + threadIdx.x, v, u8);  // same ring, 4x denser in uint8 mode
                         }
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     }
                     __syncthreads();
                     if (threadIdx.x == 0) {
                         const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(buf);
-                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst + (size_t)c * kChunkF4),
-                                     "r"(saddr), "r"((uint32_t)(kChunkF4 * sizeof(float4)))
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(obs_p + (size_t)c * chunk_bytes),
+                                     "r"(saddr), "r"(chunk_bytes)
                                      : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // chunk c-1 has left its buffer
@@ -631,34 +641,7 @@ __global__ void __launch_bounds__(32 * Wpc<OBS>::value, OBS == 0 ? ST_RAM_MINBLO
                 if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 __syncthreads();
             } else if (threadIdx.x < KPR * NG) {
-                float4 *base = reinterpret_cast<float4 *>(obs_p) + slot_k;
-#if ST_IMG_ORDER == 1
-                // Board-row major: every board row y becomes `bs` identical image rows plus `gap` grid rows, so the
-                // four selects are done once per (env, y) and reused for pitch stores (closed form of ref:99-112).
-                const unsigned img4 = (unsigned)(p.obs_elems >> 2);
-                const int pitch = p.pitch, gap = p.gap, bs = pitch - gap, top = p.pad_top;
-                const float4 vgap = make_float4(cs.lo[0], cs.lo[1], cs.lo[2], cs.lo[3]);
-                const float4 vzero = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-                for (int w = 0; w < WPC; ++w) {
-                    if (!s_active[w]) continue;
-                    float4 *img = base + (size_t)w * img4;
-                    for (int r = slot_g; r < top; r += NG) img[r * KPR] = vzero;                          // top border
-                    for (int r = top + p.inner_v + slot_g; r < kImage; r += NG) img[r * KPR] = vzero;   // bottom border
-                    for (int r = slot_g; r < gap; r += NG) img[(top + r) * KPR] = vgap;                   // first grid line
-                    for (int y = slot_g; y < H; y += NG) {
-                        const uint32_t b = s_disp[w][y];
-                        float4 v;
-                        v.x = (b & cs.mk[0]) ? cs.hi[0] : cs.lo[0];
-                        v.y = (b & cs.mk[1]) ? cs.hi[1] : cs.lo[1];
-                        v.z = (b & cs.mk[2]) ? cs.hi[2] : cs.lo[2];
-                        v.w = (b & cs.mk[3]) ? cs.hi[3] : cs.lo[3];
-                        float4 *rowp = img + (top + gap + y * pitch) * KPR;
-                        for (int r = 0; r < bs; ++r) rowp[r * KPR] = v;
-                        for (int r = bs; r < pitch; ++r) rowp[r * KPR] = vgap;
-                    }
-                }
-#else
+                const size_t img4 = (size_t)(p.obs_elems >> 2);  // 4-element groups per image
 #pragma unroll kImgUnroll
                 for (int rho = slot_g; rho < kImage; rho += NG) {
                     const int code = s_rowy[rho];
@@ -672,21 +655,13 @@ __global__ void __launch_bounds__(32 * Wpc<OBS>::value, OBS == 0 ? ST_RAM_MINBLO
                         v.z = (b & cs.mk[2]) ? cs.hi[2] : cs.lo[2];
                         v.w = (b & cs.mk[3]) ? cs.hi[3] : cs.lo[3];
                         if (code == -2) v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        float4 *dst = base + (size_t)w * (unsigned)(p.obs_elems >> 2) + rho * KPR;
-#if ST_IMG_STORE == 1
-                        __stcs(dst, v);  // streaming: written once, never re-read by this kernel
-#elif ST_IMG_STORE == 2
-                        __stwt(dst, v);
-#else
-                        *dst = v;
-#endif
+                        store4(obs_p, (size_t)w * img4 + rho * KPR + slot_k, v, u8);
                     }
                 }
-#endif
             }
             __syncthreads();
         }
-        if (MANY && obs_p) obs_p += p.obs_t_stride;
+        if (MANY && obs_p) obs_p += p.obs_t_stride * (long long)esz;
     }
 
     if (selected && MODE != MODE_OBSERVE) {

@@ -349,7 +349,8 @@ __global__ void __launch_bounds__(32 * kTpeWarps) st_step_tpe_kernel(const __gri
     // 4. observations: float32 [W][H] per env (ref:421-424, 400); 16-byte stores when H % 4 == 0, else 4-byte ones
     if (p.obs && (H & 3) != 0) {
         const int nel = W * H;
-        float *o = p.obs + (long long)t * p.obs_t_stride + e0 * (long long)p.obs_elems;
+        const bool u8 = p.obs_u8 != 0;
+        char *o = reinterpret_cast<char *>(p.obs) + ((long long)t * p.obs_t_stride + e0 * (long long)p.obs_elems) * (u8 ? 1 : 4);
         for (int i0 = 0; i0 < nel; i0 += 32) {
             const int i = i0 + lane;
             const int x = (int)(((uint32_t)i * p.inv_h20) >> 20);
@@ -357,13 +358,16 @@ __global__ void __launch_bounds__(32 * kTpeWarps) st_step_tpe_kernel(const __gri
             if (i < nel) {
                 for (int r = 0; r < nvalid; ++r) {
                     const TpeRec<RowT, ROWS16> rr = {recs + r * pitch};
-                    o[r * nel + i] = ((rr.raw(yy) >> x) & 1u) ? 1.0f : 0.0f;
+                    const bool on = ((rr.raw(yy) >> x) & 1u) != 0u;
+                    if (u8) reinterpret_cast<unsigned char *>(o)[r * nel + i] = on ? 1 : 0;
+                    else reinterpret_cast<float *>(o)[r * nel + i] = on ? 1.0f : 0.0f;
                 }
             }
         }
     } else if (p.obs) {
         const int hq = H >> 2, nq = W * hq;
-        float4 *o4 = reinterpret_cast<float4 *>(p.obs + (long long)t * p.obs_t_stride + e0 * (long long)p.obs_elems);
+        const bool u8 = p.obs_u8 != 0;
+        char *o4 = reinterpret_cast<char *>(p.obs) + ((long long)t * p.obs_t_stride + e0 * (long long)p.obs_elems) * (u8 ? 1 : 4);
         for (int q0 = 0; q0 < nq; q0 += 32) {
             const int q = q0 + lane;
             const int x = (int)(((uint32_t)q * p.inv_hq20) >> 20);
@@ -381,7 +385,7 @@ __global__ void __launch_bounds__(32 * kTpeWarps) st_step_tpe_kernel(const __gri
                         v = make_float4((rw[4 * yq] & bit) ? 1.0f : 0.0f, (rw[4 * yq + 1] & bit) ? 1.0f : 0.0f,
                                         (rw[4 * yq + 2] & bit) ? 1.0f : 0.0f, (rw[4 * yq + 3] & bit) ? 1.0f : 0.0f);
                     }
-                    o4[r * nq + q] = v;
+                    store4(o4, (size_t)(r * nq + q), v, u8);
                 }
             }
         }

@@ -23,7 +23,7 @@ class StConfig(C.Structure):
     _fields_ = [(k, C.c_int32) for k in (
         "width", "height", "obs_type", "extend_dims", "lock_delay", "step_reset", "reward_step",
         "penalise_height", "penalise_height_increase", "advanced_clears", "high_scoring", "penalise_holes",
-        "penalise_holes_increase", "auto_reset", "device", "reserved")] + [
+        "penalise_holes_increase", "auto_reset", "device", "obs_u8")] + [
         ("seed", C.c_uint64), ("env_id_base", C.c_int64)]
 
 
@@ -94,13 +94,13 @@ def check(rc: int, what: str = "simpletetris_b200"):
 
 def make_config(*, width, height, obs_type, extend_dims, lock_delay, step_reset, reward_step, penalise_height,
                 penalise_height_increase, advanced_clears, high_scoring, penalise_holes, penalise_holes_increase,
-                auto_reset, device, seed, env_id_base) -> StConfig:
+                auto_reset, device, seed, env_id_base, obs_u8=False) -> StConfig:
     # an unknown obs_type falls through to the rgb branch in the reference (tetris_env.py:432-433)
     ot = OBS_TYPES.get(obs_type, 2)
     return StConfig(int(width), int(height), ot, int(bool(extend_dims)), int(lock_delay), int(bool(step_reset)),
                     int(bool(reward_step)), int(bool(penalise_height)), int(bool(penalise_height_increase)),
                     int(bool(advanced_clears)), int(bool(high_scoring)), int(bool(penalise_holes)),
-                    int(bool(penalise_holes_increase)), int(bool(auto_reset)), int(device), 0,
+                    int(bool(penalise_holes_increase)), int(bool(auto_reset)), int(device), int(bool(obs_u8)),
                     int(seed) & (2 ** 64 - 1), int(env_id_base))
 
 

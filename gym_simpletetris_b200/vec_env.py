@@ -36,7 +36,8 @@ class VecEnv:
     def __init__(self, num_envs, width=10, height=20, obs_type="ram", extend_dims=False, render_mode="rgb_array",
                  reward_step=False, penalise_height=False, penalise_height_increase=False, advanced_clears=False,
                  high_scoring=False, penalise_holes=False, penalise_holes_increase=False, lock_delay=0,
-                 step_reset=False, *, device="cuda", seed=0, env_id_base=0, auto_reset=True, with_info=True):
+                 step_reset=False, *, device="cuda", seed=0, env_id_base=0, auto_reset=True, with_info=True,
+                 obs_dtype=torch.float32):
         self._L = native.lib()
         if not torch.cuda.is_available():
             raise RuntimeError("gym_simpletetris_b200.VecEnv needs a CUDA device (sm_100a); there is no CPU path")
@@ -49,13 +50,16 @@ class VecEnv:
         self.width, self.height, self.obs_type, self.extend_dims = width, height, obs_type, extend_dims
         self.render_mode = render_mode
         self.seed, self.env_id_base = int(seed), int(env_id_base)
+        if obs_dtype not in (torch.float32, torch.uint8):
+            raise ValueError("obs_dtype must be torch.float32 (the reference's dtype) or torch.uint8")
+        self.obs_dtype = obs_dtype  # uint8: same values, a quarter of the observation bytes (not the parity mode)
         self.cfg = native.make_config(
             width=width, height=height, obs_type=obs_type, extend_dims=extend_dims, lock_delay=lock_delay,
             step_reset=step_reset, reward_step=reward_step, penalise_height=penalise_height,
             penalise_height_increase=penalise_height_increase, advanced_clears=advanced_clears,
             high_scoring=high_scoring, penalise_holes=penalise_holes,
             penalise_holes_increase=penalise_holes_increase, auto_reset=auto_reset, device=self.device.index,
-            seed=seed, env_id_base=env_id_base)
+            seed=seed, env_id_base=env_id_base, obs_u8=obs_dtype == torch.uint8)
         stride = self._L.st_state_stride(C.byref(self.cfg))
         if stride <= 0:
             raise ValueError("unsupported geometry: width must be 1..32 and height 1..63")
@@ -65,7 +69,7 @@ class VecEnv:
                                                   extend_dims)
         n, dev = self.num_envs, self.device
         self.state = torch.zeros(n * self.state_stride, dtype=torch.uint8, device=dev)
-        self.obs = torch.zeros((n,) + self.single_observation_shape, dtype=torch.float32, device=dev)
+        self.obs = torch.zeros((n,) + self.single_observation_shape, dtype=obs_dtype, device=dev)
         self.reward = torch.zeros(n, dtype=torch.float32, device=dev)
         self.done = torch.zeros(n, dtype=torch.bool, device=dev)
         self.info_buf = torch.zeros((n, ST_INFO_WORDS), dtype=torch.int32, device=dev) if with_info else None
@@ -140,7 +144,7 @@ class VecEnv:
         n, dev = self.num_envs, self.device
         reward = torch.empty((T, n), dtype=torch.float32, device=dev)
         done = torch.empty((T, n), dtype=torch.bool, device=dev)
-        obs = torch.empty((T,) + tuple(self.obs.shape), dtype=torch.float32, device=dev) if rollout_obs else self.obs
+        obs = torch.empty((T,) + tuple(self.obs.shape), dtype=self.obs_dtype, device=dev) if rollout_obs else self.obs
         info = self.info_buf
         if rollout_info and info is not None:
             info = torch.empty((T, n, ST_INFO_WORDS), dtype=torch.int32, device=dev)

@@ -76,7 +76,9 @@ typedef struct StConfig {
     int32_t auto_reset;   /* 1: VecEnv semantics (gym<=0.25): on done, clear() (ref:306-315) in the same
                              call and return the reset observation; 0: reference single-env semantics */
     int32_t device;       /* CUDA ordinal that owns every device pointer passed with this config */
-    int32_t reserved;
+    int32_t obs_u8;       /* 0: observations are float32, as the reference returns them (ref:400) — the parity mode.
+                             1: the same values (0/1, 0/128/190) stored as uint8, 4x less observation traffic; an
+                             extension for image pipelines, benchmarked separately, never reported as the parity mode */
     uint64_t seed;        /* Philox key of the piece stream (replaces the global `random`, ref:2,187) */
     int64_t env_id_base;  /* global id of env 0 of this shard; stream of env e is keyed by base+e */
 } StConfig;
@@ -108,28 +110,28 @@ ST_API int st_init(const StConfig *cfg, void *state, int64_t n, void *stream);
 /* TetrisEnv.reset (ref:405-411) -> TetrisEngine.clear (ref:306-315) for every env (mask == NULL) or the
  * envs with mask[e] != 0.  Writes the reset observation (empty board, piece not drawn) of those envs
  * into obs (may be NULL). */
-ST_API int st_reset(const StConfig *cfg, void *state, const uint8_t *mask, float *obs, const StAux *aux,
+ST_API int st_reset(const StConfig *cfg, void *state, const uint8_t *mask, void *obs, const StAux *aux,
              int64_t n, void *stream);
 
 /* TetrisEnv.step (ref:397-403) -> TetrisEngine.step (ref:243-304) + _observation (ref:413-433) for n envs.
- *   actions [n] uint8 (ids of ref:152-160);  obs [n][st_obs_elems] float32;  reward [n] float32;
+ *   actions [n] uint8 (ids of ref:152-160);  obs [n][st_obs_elems] float32 (uint8 if cfg->obs_u8);  reward [n] float32;
  *   done [n] uint8;  info [n][ST_INFO_WORDS] int32 or NULL: piece id, lock-delay counter, time, score,
  *   lines_cleared, holes, piece_height, deaths, shape_counts[7] (get_info, ref:232-241), taken after the
  *   step and BEFORE any auto-reset. */
-ST_API int st_step(const StConfig *cfg, void *state, const uint8_t *actions, float *obs, float *reward,
+ST_API int st_step(const StConfig *cfg, void *state, const uint8_t *actions, void *obs, float *reward,
             uint8_t *done, int32_t *info, const StAux *aux, int64_t n, void *stream);
 
 /* T consecutive TetrisEnv.step calls (ref:397-403) in one launch: the caller loop of README.md:43-51 moved on the
  * device (state stays in registers between steps).  actions [T][n];
  * reward/done [T][n]; obs and info advance by obs_t_stride / info_t_stride ELEMENTS per step (0 = every
  * step overwrites the same [n][...] buffer, n*elems = a rollout buffer). */
-ST_API int st_step_many(const StConfig *cfg, void *state, const uint8_t *actions, int32_t T, float *obs,
+ST_API int st_step_many(const StConfig *cfg, void *state, const uint8_t *actions, int32_t T, void *obs,
                  int64_t obs_t_stride, float *reward, uint8_t *done, int32_t *info, int64_t info_t_stride,
                  const StAux *aux, int64_t n, void *stream);
 
 /* _observation of the current state without stepping (TetrisEngine.render, ref:317-321, when
  * draw_piece != 0; the bare board otherwise). */
-ST_API int st_observe(const StConfig *cfg, const void *state, int32_t draw_piece, float *obs, int64_t n, void *stream);
+ST_API int st_observe(const StConfig *cfg, const void *state, int32_t draw_piece, void *obs, int64_t n, void *stream);
 
 /* TetrisEnv.render('rgb_array') (ref:458-462): engine.render() -> convert_grayscale(obs, size) ->
  * convert_grayscale_rgb, uint8 out [n][size][size][3]; the reference uses size 160. */
@@ -157,9 +159,9 @@ ST_API int st_host_set_piece_queue(StHostEnv *h, const uint8_t *queue, int32_t q
 /* TetrisEnv.reset (ref:405-411) / TetrisEnv.step (ref:397-403) / engine.render() through _observation
  * (ref:317-321, 413-433) with HOST buffers, as a NumPy caller of the reference sees them.  obs/info/mask may be
  * NULL.  Copies (or maps, see st_host_set_zero_copy) the inputs in, launches, brings the results out, synchronises. */
-ST_API int st_host_reset(StHostEnv *h, const uint8_t *mask, float *obs);
-ST_API int st_host_step(StHostEnv *h, const uint8_t *actions, float *obs, float *reward, uint8_t *done, int32_t *info);
-ST_API int st_host_observe(StHostEnv *h, int32_t draw_piece, float *obs);
+ST_API int st_host_reset(StHostEnv *h, const uint8_t *mask, void *obs);
+ST_API int st_host_step(StHostEnv *h, const uint8_t *actions, void *obs, float *reward, uint8_t *done, int32_t *info);
+ST_API int st_host_observe(StHostEnv *h, int32_t draw_piece, void *obs);
 /* When a host buffer passed to st_host_step is page-locked (cudaHostAlloc / cudaHostRegister / torch
  * pin_memory), the kernel can read / write it in place over PCIe instead of staging through device memory.
  * mask = OR of ST_ZC_*; pageable buffers always take the staging path.  Default: everything in place when one

@@ -453,3 +453,40 @@ def test_checkpoint_resume(st):
     assert other.episode_stats(reduce=False) == env.episode_stats(reduce=False)
     with pytest.raises(ValueError):
         st.VecEnv(n, device="cuda:0", seed=22, **kw).load_state_dict(sd)
+
+
+# ---- uint8 observation mode (extension; the float32 mode above is the parity mode) --------------------------
+@pytest.mark.parametrize("kw,n", [
+    (dict(reward_step=True), 300), (dict(width=7, height=9), 70), (dict(width=20, height=40), 33),
+    (dict(obs_type="grayscale", extend_dims=True), 37), (dict(obs_type="rgb"), 37), (dict(obs_type="rgb", width=6, height=12), 16),
+    (dict(obs_type="grayscale", width=20, height=40), 9),
+])
+def test_uint8_observations_equal_float32_cast(st, kw, n):
+    a = st.VecEnv(n, device="cuda:0", seed=31, **kw)
+    b = st.VecEnv(n, device="cuda:0", seed=31, obs_dtype=torch.uint8, **kw)
+    oa, ob = a.reset(), b.reset()
+    assert ob.dtype == torch.uint8 and ob.shape == oa.shape and torch.equal(ob, oa.to(torch.uint8))
+    rs = np.random.RandomState(8)
+    for t in range(80):
+        act = torch.from_numpy(rs.randint(0, 7, n).astype(np.uint8)).cuda()
+        (oa, ra, da, _), (ob, rb, db, _) = a.step(act), b.step(act)
+        assert torch.equal(ob, oa.to(torch.uint8)) and torch.equal(ra, rb) and torch.equal(da, db), t
+    assert torch.equal(b.observe(True), a.observe(True).to(torch.uint8))
+    if kw.get("obs_type", "ram") == "ram":
+        T = 12
+        acts = torch.from_numpy(rs.randint(0, 7, (T, n)).astype(np.uint8)).cuda()
+        oa, _, _, _ = a.step_many(acts, rollout_obs=True)
+        ob, _, _, _ = b.step_many(acts, rollout_obs=True)
+        assert torch.equal(ob, oa.to(torch.uint8))
+
+
+def test_uint8_full_batch_images(st):
+    """Eight-env CTAs all active: the rgb bulk-store ring in uint8 mode, plus a ragged tail."""
+    for n in (64, 67):
+        a = st.VecEnv(n, device="cuda:0", seed=5, obs_type="rgb")
+        b = st.VecEnv(n, device="cuda:0", seed=5, obs_type="rgb", obs_dtype=torch.uint8)
+        a.reset(), b.reset()
+        hard = torch.full((n,), 2, dtype=torch.uint8, device="cuda")
+        for _ in range(25):
+            oa, ob = a.step(hard)[0], b.step(hard)[0]
+            assert torch.equal(ob, oa.to(torch.uint8))

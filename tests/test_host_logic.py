@@ -36,8 +36,7 @@ def test_config_marshalling_round_trip():
     L = native.lib()
     assert L.st_state_stride(C.byref(cfg)) == 60 + 24 * 2
     assert L.st_step_kernel_name(C.byref(cfg), 4096).decode().startswith("st_main_kernel<grayscale")
-    ram = native.make_config(**{**{f[0]: getattr(cfg, f[0]) for f in cfg._fields_ if f[0] != "reserved"},
-                                "obs_type": "ram"})
+    ram = native.make_config(**{**{f[0]: getattr(cfg, f[0]) for f in cfg._fields_}, "obs_type": "ram"})
     assert L.st_step_kernel_name(C.byref(ram), 4096).decode() == "st_main_kernel<ram,STEP>"
     assert L.st_step_kernel_name(C.byref(ram), 1 << 20).decode() == "st_step_tpe_kernel"
 

@@ -393,6 +393,24 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def ensure_built(rank):
+    """A checkout without the in-tree .so (it is git-ignored): rank 0 compiles it (nvcc, ~30 s), the others wait."""
+    so = os.path.join(ROOT, "gym_simpletetris_b200", "libsimpletetris_b200.so")
+    if os.path.exists(so):
+        return
+    if rank == 0:
+        import __graft_entry__
+
+        __graft_entry__.build()
+    else:
+        for _ in range(600):
+            if os.path.exists(so):
+                time.sleep(1.0)  # let the linker finish writing
+                return
+            time.sleep(0.5)
+        raise SystemExit("bench.py: libsimpletetris_b200.so was not built")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -410,11 +428,13 @@ def main():
     if args.impl == "reference":
         return reference_arm(args)
 
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    ensure_built(rank)
+
     import torch
     import torch.distributed as dist
 
-    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
-    local = int(os.environ.get("LOCAL_RANK", 0))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product has no CPU path; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)

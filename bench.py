@@ -405,7 +405,6 @@ def ensure_built(rank):
     else:
         for _ in range(600):
             if os.path.exists(so):
-                time.sleep(1.0)  # let the linker finish writing
                 return
             time.sleep(0.5)
         raise SystemExit("bench.py: libsimpletetris_b200.so was not built")

@@ -12,7 +12,6 @@ constexpr int kWarpsPerCta = 8;       // image modes: one env per warp, 8 envs p
 #define ST_RAM_WARPS 4
 #endif
 constexpr int kRamWarpsPerCta = ST_RAM_WARPS;  // ram mode
-constexpr int kThreads = 32 * kWarpsPerCta;
 constexpr int kImage = 84;            // ref:426: _observation always renders at 84
 constexpr int kStateWords = 15;
 

@@ -13,7 +13,10 @@
 // nothing when they are not taken.
 // Observations: ram is expanded by the env's own warp from a smem staging row with 16-byte stores;
 // 84x84 images are written by the whole CTA (8 envs) with every thread owning a fixed 16-byte column
-// slot, so a warp store covers 512 contiguous bytes.
+// slot, so a warp store covers 512 contiguous bytes; rgb leaves through TMA bulk stores from a shared-memory ring.
+// Large ram batches take the thread-per-env kernel of st_kernels_tpe.cuh instead (see launch_main).
+//
+// Compile-time tuning knobs (defaults are the measured best on B200; DESIGN.md section 6 lists what was tried).
 #include "st_internal.h"
 
 #include <cstdlib>

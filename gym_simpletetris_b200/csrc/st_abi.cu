@@ -76,6 +76,7 @@ int make_params(const StConfig *c, const StAux *aux, int64_t n, st::Params *out)
         p.queue_len = aux->queue_len;
         p.err = aux->error_flag;
         p.stats = aux->stats;
+        p.term_obs = aux->terminal_obs;
         if (p.queue && p.queue_len <= 0) return fail(ST_E_INVALID, "piece_queue with queue_len <= 0%s");
     }
     p.n = n;

@@ -38,6 +38,7 @@ struct Params {
     const uint8_t *actions;
     void *obs;       // float32 [n][obs_elems], or uint8 when obs_u8
     int obs_u8;
+    void *term_obs;  // optional [n][obs_elems]: terminal observation of auto-reset envs
     float *reward;
     uint8_t *done;
     int32_t *info;

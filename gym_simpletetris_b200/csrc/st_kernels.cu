@@ -473,6 +473,9 @@ __global__ void __launch_bounds__(32 * Wpc<OBS>::value, OBS == 0 ? ST_RAM_MINBLO
     __shared__ __align__(16) uint32_t s_disp[WPC][32 * RPL];
     __shared__ signed char s_rowy[OBS == 0 ? 1 : kImage];
     __shared__ unsigned char s_active[WPC];
+    // terminal observation of envs that are auto-reset in this step (gym<=0.25 vector semantics: info["terminal_observation"])
+    __shared__ __align__(16) uint32_t s_term[WPC][32 * RPL];
+    __shared__ unsigned char s_has_term[WPC];
     // rgb: the CTA's output leaves through TMA bulk stores from a 3-deep ring of shared-memory chunks (measured
     // +5 % over direct 16-byte stores); grayscale and ram keep direct stores (bulk stores measured 8 % slower there)
     constexpr bool kBulk = OBS == 2 && ST_IMG_BULK != 0;
@@ -539,6 +542,9 @@ __global__ void __launch_bounds__(32 * Wpc<OBS>::value, OBS == 0 ? ST_RAM_MINBLO
     const size_t esz = u8 ? 1 : 4;  // bytes per observation element
     char *obs_p = p.obs ? reinterpret_cast<char *>(p.obs) + (size_t)(OBS == 0 ? e : (int)blockIdx.x * WPC) * (unsigned)p.obs_elems * esz
                         : nullptr;
+    char *term_p = (MODE == MODE_STEP && p.term_obs)
+                       ? reinterpret_cast<char *>(p.term_obs) + (size_t)(OBS == 0 ? e : (int)blockIdx.x * WPC) * (unsigned)p.obs_elems * esz
+                       : nullptr;
     int action = (int)action_u;
     if (selected) pc = unpack_piece(get(sw, 0));
 #pragma unroll
@@ -546,6 +552,7 @@ __global__ void __launch_bounds__(32 * Wpc<OBS>::value, OBS == 0 ? ST_RAM_MINBLO
 
     const int T = (MODE == MODE_STEP && MANY) ? p.T : 1;  // single-step launches compile without the step loop
     for (int t = 0; t < T; ++t) {
+        bool has_term = false;
         if (selected) {
             if (MODE == MODE_STEP) {
                 int reward = 0, done = 0;
@@ -557,6 +564,11 @@ __global__ void __launch_bounds__(32 * Wpc<OBS>::value, OBS == 0 ? ST_RAM_MINBLO
                         atomicAdd(p.stats + (lane == 2 ? 1 : lane == 3 ? 3 : 2), (unsigned long long)(long long)sw);
                     if (p.stats && lane == 0) atomicAdd(p.stats, 1ull);
                     if (p.auto_reset) {  // VecEnv: reset obs = empty board, piece not drawn (ref:313-315)
+                        if (term_p) {  // what step() returned in the reference at this terminal step (ref:301-302)
+#pragma unroll
+                            for (int k = 0; k < RPL; ++k) s_term[warp][lane + 32 * k] = (uint32_t)(disp[k] >> OFF) & p.fullmask;
+                            has_term = true;
+                        }
                         engine_clear<RPL, RowT>(row, sw, pc, lane, p, e, errbits, walls);
                         put(sw, lane, 0, pack_piece(pc));
 #pragma unroll
@@ -596,9 +608,13 @@ __global__ void __launch_bounds__(32 * Wpc<OBS>::value, OBS == 0 ? ST_RAM_MINBLO
         if (OBS == 0) {
             __syncwarp();
             if (selected && obs_p) write_ram(s_disp[warp], obs_p, p, lane);  // unselected (masked-out) envs keep their obs
+            if (has_term) write_ram(s_term[warp], term_p, p, lane);
             __syncwarp();
         } else {
-            if (lane == 0) s_active[warp] = selected && obs_p;
+            if (lane == 0) {
+                s_active[warp] = selected && obs_p;
+                s_has_term[warp] = has_term;
+            }
             __syncthreads();
             // TMA bulk-store path: the CTA's 8 images are one contiguous region; it is produced in chunks of
             // kBulkPasses x 252 float4 in shared memory (3 buffers) and each chunk leaves with one
@@ -662,8 +678,27 @@ __global__ void __launch_bounds__(32 * Wpc<OBS>::value, OBS == 0 ? ST_RAM_MINBLO
                     }
                 }
             }
+            if (MODE == MODE_STEP && term_p && threadIdx.x < KPR * NG) {  // rare: images of the envs that just ended
+                const size_t img4 = (size_t)(p.obs_elems >> 2);
+#pragma unroll 1
+                for (int w = 0; w < WPC; ++w) {
+                    if (!s_has_term[w]) continue;
+                    for (int rho = slot_g; rho < kImage; rho += NG) {
+                        const int code = s_rowy[rho];
+                        const uint32_t b = code >= 0 ? s_term[w][code] : 0u;
+                        float4 v;
+                        v.x = (b & cs.mk[0]) ? cs.hi[0] : cs.lo[0];
+                        v.y = (b & cs.mk[1]) ? cs.hi[1] : cs.lo[1];
+                        v.z = (b & cs.mk[2]) ? cs.hi[2] : cs.lo[2];
+                        v.w = (b & cs.mk[3]) ? cs.hi[3] : cs.lo[3];
+                        if (code == -2) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        store4(term_p, (size_t)w * img4 + rho * KPR + slot_k, v, u8);
+                    }
+                }
+            }
             __syncthreads();
         }
+        if (MANY && term_p) term_p += p.obs_t_stride * (long long)esz;
         if (MANY && obs_p) obs_p += p.obs_t_stride * (long long)esz;
     }
 

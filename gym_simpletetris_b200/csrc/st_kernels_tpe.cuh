@@ -319,6 +319,26 @@ __global__ void __launch_bounds__(32 * kTpeWarps) st_step_tpe_kernel(const __gri
         }
     }
     __syncwarp();
+    if (p.term_obs) {  // terminal observation of the envs that end here: their board already holds the locked piece
+        unsigned term = __ballot_sync(FULL, lane < nvalid && done && p.auto_reset);
+        const bool u8 = p.obs_u8 != 0;
+        char *tb = reinterpret_cast<char *>(p.term_obs) + ((long long)t * p.obs_t_stride + e0 * (long long)p.obs_elems) * (u8 ? 1 : 4);
+        const int nel = W * H;
+        while (term) {
+            const int r = __ffs((int)term) - 1;
+            term &= term - 1;
+            const TpeRec<RowT, ROWS16> rr = {recs + r * pitch};
+            char *dst = tb + (size_t)r * nel * (u8 ? 1 : 4);
+            for (int i = lane; i < nel; i += 32) {
+                const int x = (int)(((uint32_t)i * p.inv_h20) >> 20);
+                const int yy = i - x * H;
+                const bool on = ((rr.raw(yy) >> x) & 1u) != 0u;
+                if (u8) reinterpret_cast<unsigned char *>(dst)[i] = on ? 1 : 0;
+                else reinterpret_cast<float *>(dst)[i] = on ? 1.0f : 0.0f;
+            }
+        }
+        __syncwarp();
+    }
     uint32_t pbits[4] = {0u, 0u, 0u, 0u};
     int ptop = 0;
     if (lane < nvalid) {

@@ -29,7 +29,7 @@ class StConfig(C.Structure):
 
 class StAux(C.Structure):
     _fields_ = [("piece_queue", C.c_void_p), ("queue_len", C.c_int32), ("reserved", C.c_int32),
-                ("error_flag", C.c_void_p), ("stats", C.c_void_p)]
+                ("error_flag", C.c_void_p), ("stats", C.c_void_p), ("terminal_obs", C.c_void_p)]
 
 
 # every symbol include/simpletetris_b200.h declares: name -> (restype, argtypes)

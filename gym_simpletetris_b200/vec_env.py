@@ -37,7 +37,7 @@ class VecEnv:
                  reward_step=False, penalise_height=False, penalise_height_increase=False, advanced_clears=False,
                  high_scoring=False, penalise_holes=False, penalise_holes_increase=False, lock_delay=0,
                  step_reset=False, *, device="cuda", seed=0, env_id_base=0, auto_reset=True, with_info=True,
-                 obs_dtype=torch.float32):
+                 obs_dtype=torch.float32, terminal_obs=False):
         self._L = native.lib()
         if not torch.cuda.is_available():
             raise RuntimeError("gym_simpletetris_b200.VecEnv needs a CUDA device (sm_100a); there is no CPU path")
@@ -76,7 +76,11 @@ class VecEnv:
         self.err = torch.zeros(1, dtype=torch.int32, device=dev)
         self.stats = torch.zeros(ST_STATS_WORDS, dtype=torch.int64, device=dev)
         self._queue = None
-        self._aux = StAux(None, 0, 0, self.err.data_ptr(), self.stats.data_ptr())
+        # gym<=0.25 vector envs report the last observation of a finished episode in info["terminal_observation"]
+        # (the returned obs is already the reset one); optional because it is a second observation-sized buffer
+        self.term_obs = torch.zeros_like(self.obs) if (terminal_obs and auto_reset) else None
+        self._aux = StAux(None, 0, 0, self.err.data_ptr(), self.stats.data_ptr(),
+                          self.term_obs.data_ptr() if self.term_obs is not None else None)
         # per-step host cost matters for small batches: everything constant across steps is bound once
         self._cfg_ref, self._aux_ref = C.byref(self.cfg), C.byref(self._aux)
         self._info_views = self._info(self.info_buf)
@@ -112,6 +116,8 @@ class VecEnv:
             return {}
         d = {k: buf[..., INFO_COLS[k]] for k in INFO_KEYS if k != "statistics"}
         d["statistics"] = buf[..., 8:15]
+        if getattr(self, "term_obs", None) is not None and buf is self.info_buf:
+            d["terminal_observation"] = self.term_obs  # rows are valid where `done` is set in the same step
         return d
 
     # ---- the reference API, batched ----
@@ -152,7 +158,7 @@ class VecEnv:
             C.byref(self.cfg), self.state.data_ptr(), a.data_ptr(), T, obs.data_ptr(),
             n * self.obs_elems if rollout_obs else 0, reward.data_ptr(), done.data_ptr(),
             info.data_ptr() if info is not None else None, n * ST_INFO_WORDS if rollout_info else 0,
-            C.byref(self._aux), n, self._stream()), "st_step_many")
+            C.byref(self._aux_many()), n, self._stream()), "st_step_many")
         return obs, reward, done, self._info(info)
 
     def capture_step(self):
@@ -160,6 +166,11 @@ class VecEnv:
         given actions into a static device buffer and replays the graph — no per-step ctypes/launch cost on the
         host, so a device-resident policy can drive small batches at kernel rate."""
         return GraphedStep(self)
+
+    def _aux_many(self):
+        """StAux for st_step_many: no terminal-observation buffer (it is sized for one step; use step() for those)."""
+        a = self._aux
+        return StAux(a.piece_queue, a.queue_len, 0, a.error_flag, a.stats, None)
 
     def observe(self, draw_piece=True):
         """_observation(engine.render()) (tetris_env.py:317-321, 413-433) of the current state, no step."""

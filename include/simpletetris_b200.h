@@ -93,6 +93,10 @@ typedef struct StAux {
     int32_t *error_flag;        /* device int32, sticky OR of ST_ERR_* */
     unsigned long long *stats;  /* device u64[ST_STATS_WORDS]: episodes, sum(time), sum(lines_cleared),
                                    sum(score) accumulated at every done */
+    void *terminal_obs;         /* [n][st_obs_elems], same dtype as obs: with auto_reset, the observation the
+                                   reference's step() returned at the terminal step (ref:301-304) is written
+                                   here for the envs that are done in this call (gym <= 0.25 vector envs put it
+                                   in info["terminal_observation"]); rows of other envs are left untouched */
 } StAux;
 
 /* ---- sizes ------------------------------------------------------------------ */

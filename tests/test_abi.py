@@ -45,7 +45,7 @@ def test_sizes_follow_survey_accounting():
 
 def test_struct_layout_matches_header():
     assert C.sizeof(native.StConfig) == 16 * 4 + 16
-    assert C.sizeof(native.StAux) == 8 + 8 + 8 + 8
+    assert C.sizeof(native.StAux) == 8 + 8 + 8 + 8 + 8
 
 
 def test_no_cpu_fallback():

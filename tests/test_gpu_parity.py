@@ -490,3 +490,34 @@ def test_uint8_full_batch_images(st):
         for _ in range(25):
             oa, ob = a.step(hard)[0], b.step(hard)[0]
             assert torch.equal(ob, oa.to(torch.uint8))
+
+
+@pytest.mark.parametrize("kw,n", [
+    (dict(reward_step=True), 96), (dict(width=4, height=8, lock_delay=1), 150), (dict(width=20, height=40), 40),
+    (dict(obs_type="grayscale", width=6, height=10), 24), (dict(obs_type="rgb", width=5, height=8), 19),
+])
+def test_terminal_observation(st, kw, n):
+    """info["terminal_observation"][e] at a done step == what the reference's step() returned at that step."""
+    from oracle.oracle import OracleEnv
+
+    T = 150
+    env = st.VecEnv(n, device="cuda:0", seed=13, terminal_obs=True, **kw)
+    env.reset()
+    rs = np.random.RandomState(6)
+    acts = rs.choice(7, size=(T, n), p=[0.1, 0.1, 0.4, 0.1, 0.1, 0.1, 0.1]).astype(np.uint8)
+    got = []
+    for t in range(T):
+        obs, r, d, info = env.step(torch.from_numpy(acts[t]).cuda())
+        dn = d.cpu().numpy()
+        got.append((dn, info["terminal_observation"].cpu().numpy()[dn].copy(), obs.cpu().numpy()[dn].copy()))
+    assert sum(int(g[0].sum()) for g in got) > n // 2  # plenty of episode ends
+    for e in range(min(n, 24)):
+        o = OracleEnv(seed=13, env_id=e, **kw)
+        o.reset()
+        for t in range(T):
+            last, r, d, _ = o.step(int(acts[t, e]))
+            assert d == bool(got[t][0][e])
+            if d:
+                k = int(got[t][0][:e].sum())
+                assert np.array_equal(got[t][1][k], last), (e, t)          # terminal observation
+                assert np.array_equal(got[t][2][k], o.reset()), (e, t)     # returned obs is the reset one

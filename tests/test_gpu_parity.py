@@ -521,3 +521,31 @@ def test_terminal_observation(st, kw, n):
                 k = int(got[t][0][:e].sum())
                 assert np.array_equal(got[t][1][k], last), (e, t)          # terminal observation
                 assert np.array_equal(got[t][2][k], o.reset()), (e, t)     # returned obs is the reset one
+
+
+def test_facade_surface_matches_reference_class(st):
+    """Attributes, spaces and reset/step signatures of tetris_env.py:338-433 on the drop-in class."""
+    for kw, shape in ((dict(), (10, 20)), (dict(extend_dims=True), (10, 20, 1)),
+                      (dict(obs_type="grayscale"), (84, 84)), (dict(obs_type="grayscale", extend_dims=True), (84, 84, 1)),
+                      (dict(obs_type="rgb", width=8, height=14), (84, 84, 3))):
+        env = st.make("SimpleTetris-v0", lock_delay=2, reward_step=True, **kw)
+        assert (env.width, env.height) == (kw.get("width", 10), kw.get("height", 20))
+        assert env.obs_type == kw.get("obs_type", "ram") and env.extend_dims == kw.get("extend_dims", False)
+        assert env.render_mode == "rgb_array" and env.window_size == 512
+        assert env.action_space.n == 7 and tuple(env.observation_space.shape) == shape
+        assert np.dtype(env.observation_space.dtype) == np.float32
+        obs, info = env.reset(return_info=True)
+        assert obs.shape == shape and obs.dtype == np.float32 and not (obs == 190).any() and obs.max() <= 128
+        assert set(info) == {"time", "current_piece", "score", "lines_cleared", "holes", "deaths", "statistics"}
+        assert info["time"] == 0 and info["score"] == 0 and info["deaths"] == 0
+        assert sum(info["statistics"].values()) == 1 and info["statistics"][info["current_piece"]] == 1
+        assert env.engine.anchor == (env.width // 2, 0) and env.engine.shape_name == info["current_piece"]
+        obs, reward, done, info = env.step(6)
+        assert isinstance(reward, (int, float)) and reward == 1 and done is False and info["time"] == 1
+        assert obs.shape == shape and (obs != 0).any()
+        assert env.engine.anchor == (env.width // 2, 1)  # gravity (ref:247)
+        frame = env.render(mode="rgb_array")
+        assert frame.shape == (160, 160, 3) and frame.dtype == np.uint8
+        env.close()
+    odd = st.make("SimpleTetris-v0", obs_type="bogus")  # ref:381-392 sets no space, ref:432-433 renders rgb
+    assert not hasattr(odd, "observation_space") and odd.reset().shape == (84, 84, 3)

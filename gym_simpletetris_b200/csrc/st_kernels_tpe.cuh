@@ -481,7 +481,7 @@ static cudaError_t launch_tpe(const Params &p0, cudaStream_t stream)
     // envs per warp: the per-warp engine chain is the same for 8 or 32 envs, so mid-size batches get more warps
     const char *ov = getenv("ST_B200_TPE_EPW");
     p.tpe_epw = ov ? atoi(ov) : tpe_default_epw(p);
-    if (p.tpe_epw != 8 && p.tpe_epw != 16 && p.tpe_epw != 32) p.tpe_epw = 32;
+    if (p.tpe_epw != 4 && p.tpe_epw != 8 && p.tpe_epw != 16 && p.tpe_epw != 32) p.tpe_epw = 32;
     const bool wide = p.W + OFF + 3 > 31;
     if (p.row_bytes == 2) return launch_tpe_t<uint32_t, true>(p, stream);  // W <= 16 is never wide
     if (!wide) return launch_tpe_t<uint32_t, false>(p, stream);

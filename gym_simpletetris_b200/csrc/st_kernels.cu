@@ -26,6 +26,9 @@ namespace st {
 #ifndef ST_FORCE_MANY
 #define ST_FORCE_MANY 0
 #endif
+#ifndef ST_ANCHOR_PTRS
+#define ST_ANCHOR_PTRS 0
+#endif
 #ifndef ST_RAM_MINBLOCKS
 #define ST_RAM_MINBLOCKS 1
 #endif
@@ -545,6 +548,11 @@ __global__ void __launch_bounds__(32 * Wpc<OBS>::value, OBS == 0 ? ST_RAM_MINBLO
     char *term_p = (MODE == MODE_STEP && p.term_obs)
                        ? reinterpret_cast<char *>(p.term_obs) + (size_t)(OBS == 0 ? e : (int)blockIdx.x * WPC) * (unsigned)p.obs_elems * esz
                        : nullptr;
+#if ST_ANCHOR_PTRS
+    // Materialise the output addresses now, while the state loads are in flight (the compiler would otherwise sink
+    // this arithmetic to the stores at the end of the step, behind the whole dependent chain).
+    asm volatile("" : "+l"(rew_p), "+l"(done_p), "+l"(info_p), "+l"(obs_p));
+#endif
     int action = (int)action_u;
     if (selected) pc = unpack_piece(get(sw, 0));
 #pragma unroll
@@ -838,7 +846,10 @@ __global__ void __launch_bounds__(256) st_render_kernel(const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
-constexpr long long kSmallRamBatch = 6144;
+#ifndef ST_SMALL_RAM_BATCH
+#define ST_SMALL_RAM_BATCH 6144
+#endif
+constexpr long long kSmallRamBatch = ST_SMALL_RAM_BATCH;
 static unsigned long long g_launches = 0;
 unsigned long long launch_count() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 static inline void count_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }

@@ -50,7 +50,7 @@ WORKLOADS = {
 # `ncu --set full` captures summarised in profiles/r1_<workload>_step_kernel_ncu_full.txt.  ncu flushes caches
 # before the single replayed launch and stops at kernel end, so writes still sitting in the 126 MB L2 are not
 # counted: the small ram workloads read their state from DRAM but their observations stay in L2.
-NCU_TRAFFIC_BYTES = {"C2": 443904 + 0, "C3": 19730432 + 343011072, "C4": 27280128 + 7380526000, "C5a": 19096832 + 11059024000, "C5b": 14553344 + 170826752}
+NCU_TRAFFIC_BYTES = {"C2": 443904 + 0, "C3": 6681856 + 8695296, "C4": 27280128 + 7380526000, "C5a": 19096832 + 11059024000, "C5b": 14555136 + 171936512}
 # uint8-observation extension (same values, a quarter of the observation bytes): reported separately, with its own
 # algorithmic bytes, and only when asked for with --modes ...,C4_u8,C5a_u8 or --modes all+u8
 U8_WORKLOADS = {

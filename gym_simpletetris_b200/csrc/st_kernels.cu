@@ -41,6 +41,9 @@ namespace st {
 #ifndef ST_IMG_BULK
 #define ST_IMG_BULK 1
 #endif
+#ifndef ST_IMG_BULK_GRAY
+#define ST_IMG_BULK_GRAY 0
+#endif
 #ifndef ST_IMG_BULK_PASSES
 #define ST_IMG_BULK_PASSES 2
 #endif
@@ -481,7 +484,7 @@ __global__ void __launch_bounds__(32 * Wpc<OBS>::value, OBS == 0 ? ST_RAM_MINBLO
     __shared__ unsigned char s_has_term[WPC];
     // rgb: the CTA's output leaves through TMA bulk stores from a 3-deep ring of shared-memory chunks (measured
     // +5 % over direct 16-byte stores); grayscale and ram keep direct stores (bulk stores measured 8 % slower there)
-    constexpr bool kBulk = OBS == 2 && ST_IMG_BULK != 0;
+    constexpr bool kBulk = (OBS == 2 || (OBS == 1 && ST_IMG_BULK_GRAY != 0)) && ST_IMG_BULK != 0;
     constexpr int kBulkPasses = ST_IMG_BULK_PASSES;
     __shared__ __align__(128) float4 s_bulk[kBulk ? 3 : 1][kBulk ? kBulkPasses * 252 : 1];
 

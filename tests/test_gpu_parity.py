@@ -549,3 +549,38 @@ def test_facade_surface_matches_reference_class(st):
         env.close()
     odd = st.make("SimpleTetris-v0", obs_type="bogus")  # ref:381-392 sets no space, ref:432-433 renders rgb
     assert not hasattr(odd, "observation_space") and odd.reset().shape == (84, 84, 3)
+
+
+def test_many_full_rows_at_once(st):
+    """Injected boards with up to ~10 full rows (unreachable in play, but `_clear_lines` (ref:205-216) handles any
+    count): one hard drop of a vertical I, every env compared with the oracle."""
+    from oracle.oracle import OracleEnv
+
+    for (W, H) in ((10, 20), (6, 40), (20, 24)):
+        n = 64
+        rs = np.random.RandomState(W * H)
+        boards = (rs.rand(n, W, H) < 0.5).astype(np.uint8)
+        for e in range(n):
+            full = rs.rand(H) < 0.3
+            boards[e][:, full] = 1
+        boards[:, :, :4] = 0
+        boards[:, W // 2, :] = 0
+        kw = dict(width=W, height=H, penalise_height_increase=True, penalise_holes_increase=True, high_scoring=True)
+        env = st.VecEnv(n, device="cuda:0", seed=1, **kw)
+        env.set_piece_queue(np.tile(np.array([5, 6, 6, 6], np.uint8), (n, 1)))  # I, then O
+        env.reset()
+        env.set_state(boards=boards)
+        obs, r, d, info = env.step(torch.full((n,), 2, dtype=torch.uint8))
+        got_info = env.info_buf.cpu().numpy()[:, INFO13]
+        got_boards = env.get_state()[0].cpu().numpy()
+        for e in range(n):
+            o = OracleEnv(pieces=["I", "O", "O", "O"], **kw)
+            o.reset()
+            o.board = boards[e].astype(np.float64)
+            want, rr, dd, winfo = o.step(2)
+            if dd:
+                want = o.reset()
+            assert float(r[e]) == rr and bool(d[e]) == dd, (W, H, e)
+            assert got_info[e].tolist() == info_row(winfo), (W, H, e)
+            assert np.array_equal(obs[e].cpu().numpy(), want), (W, H, e)
+            assert np.array_equal(got_boards[e], o.board.astype(np.uint8)), (W, H, e)

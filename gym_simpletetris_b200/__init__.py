@@ -9,6 +9,7 @@ gym_simpletetris/__init__.py:3-6 does, so `gym.make('SimpleTetris-v0', **kwargs)
 """
 from . import native  # noqa: F401
 from .envs import TetrisEnv, TetrisEnvV26  # noqa: F401
+from .host_env import HostVecEnv  # noqa: F401
 from .sharding import all_reduce_sum, make_sharded_vec_env, shard_bounds  # noqa: F401
 from .vec_env import SHAPE_NAMES, VecEnv  # noqa: F401
 

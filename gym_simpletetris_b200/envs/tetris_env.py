@@ -107,6 +107,26 @@ class EngineView:
     def get_info(self):
         return self._env._get_info()
 
+    def render(self):
+        """TetrisEngine.render (tetris_env.py:317-321): copy of the board with the active piece drawn."""
+        s = self._scalars()
+        if s[0] >= 7:
+            raise TypeError("'NoneType' object is not iterable")  # shape is None before the first reset (ref:170-172)
+        state = self.board
+        for i, j in self.shape:  # _set_piece(True), tetris_env.py:323-327: in-board cells only
+            x, y = i + int(s[2]), j + int(s[3])
+            if 0 <= x < self.width and 0 <= y < self.height:
+                state[x, y] = 1.0
+        return state
+
+    def __repr__(self):
+        """The ASCII dump of tetris_env.py:329-335, byte for byte: board with the piece drawn, one text row per y."""
+        state = self.render()
+        s = "o" + "-" * self.width + "o\n"
+        s += "\n".join(["|" + "".join(["X" if j else " " for j in i]) + "|" for i in state.T])
+        s += "\no" + "-" * self.width + "o"
+        return s
+
 
 class TetrisEnv(_Base):
     metadata = {"render.modes": ["human", "rgb_array"], "render_fps": 8}  # tetris_env.py:339
@@ -205,16 +225,39 @@ class TetrisEnv(_Base):
         native.check(self._L.st_host_observe(self._h, 1, obs.ctypes.data), "st_host_observe")
         return obs
 
+    def _render_frame(self, size):
+        out = np.empty((size, size, 3), dtype=np.uint8)
+        native.check(self._L.st_host_render(self._h, 1, size, out.ctypes.data), "st_host_render")
+        return out
+
     def render(self, mode="human"):
         """mode='rgb_array': uint8 (160, 160, 3) image of the board with the active piece (tetris_env.py:458-462),
-        written by the `st_render` kernel.  mode='human' needs a pygame window (tetris_env.py:437-457): out of
-        scope here (display, not step path)."""
+        written by the `st_render` kernel.  mode='human' (tetris_env.py:437-457): the same writer at window_size,
+        shown in a pygame window; pygame is imported here, on first use, so the step path never needs it."""
         if mode == "rgb_array":
-            out = np.empty((160, 160, 3), dtype=np.uint8)
-            native.check(self._L.st_host_render(self._h, 1, 160, out.ctypes.data), "st_host_render")
-            return out
+            return self._render_frame(160)
         if mode == "human":
-            raise NotImplementedError("render('human') opens a pygame window; only 'rgb_array' is provided")
+            try:
+                import pygame
+            except ImportError as e:
+                raise ImportError("render('human') needs pygame (pygame>=2.1.0, as the reference's setup.py:20 "
+                                  "requires); render('rgb_array') does not") from e
+            if self.window is None:
+                pygame.init()
+                pygame.display.init()
+                self.window = pygame.display.set_mode((self.window_size, self.window_size))
+            if self.clock is None:
+                self.clock = pygame.time.Clock()
+            # ref:444-447 renders the TRANSPOSED board: convert_grayscale(board.T, S) == convert_grayscale(board, S).T,
+            # which is what pygame's [x][y] surface arrays want
+            obs = np.ascontiguousarray(self._render_frame(self.window_size).transpose(1, 0, 2))
+            pygame.pixelcopy.array_to_surface(self.window, obs)
+            canvas = pygame.surfarray.make_surface(obs)
+            self.window.blit(canvas, canvas.get_rect())
+            pygame.event.pump()
+            pygame.display.update()
+            self.clock.tick(self.metadata["render_fps"])
+            return None
         return None  # the reference defers to gym.Env.render, which does nothing for unknown modes
 
     def close(self):

@@ -52,6 +52,8 @@ SYMBOLS = {
     "st_host_reset": (C.c_int, [_P, _P, _P]),
     "st_host_step": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "st_host_observe": (C.c_int, [_P, _I32, _P]),
+    "st_host_step_async": (C.c_int, [_P, _P]),
+    "st_host_wait": (C.c_int, [_P, _P, _P, _P, _P]),
     "st_host_set_zero_copy": (C.c_int, [_P, _I32]),
     "st_host_set_seed": (C.c_int, [_P, C.c_uint64]),
     "st_host_alloc_pinned": (_P, [C.c_size_t]),

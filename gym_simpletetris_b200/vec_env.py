@@ -87,6 +87,7 @@ class VecEnv:
         self._ptrs = (self.state.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
                       self.info_buf.data_ptr() if self.info_buf is not None else None)
         self._st_step = self._L.st_step
+        self._closed = False
         self._check(self._L.st_init(C.byref(self.cfg), self.state.data_ptr(), n, self._stream()), "st_init")
 
     # ---- plumbing ----
@@ -110,19 +111,24 @@ class VecEnv:
             raise ValueError(f"actions must have shape {shape}, got {tuple(actions.shape)}")
         return actions
 
-    def _info(self, buf=None):
+    def _info(self, buf=None, terminal=True):
         buf = self.info_buf if buf is None else buf
         if buf is None:
             return {}
         d = {k: buf[..., INFO_COLS[k]] for k in INFO_KEYS if k != "statistics"}
         d["statistics"] = buf[..., 8:15]
-        if getattr(self, "term_obs", None) is not None and buf is self.info_buf:
+        if terminal and getattr(self, "term_obs", None) is not None and buf is self.info_buf:
             d["terminal_observation"] = self.term_obs  # rows are valid where `done` is set in the same step
         return d
+
+    def _live(self):
+        if self._closed:  # the reference deletes its engine in close() (tetris_env.py:466-467): later calls raise
+            raise RuntimeError("VecEnv is closed")
 
     # ---- the reference API, batched ----
     def reset(self, mask=None):
         """TetrisEnv.reset (tetris_env.py:405-411) for all envs, or those with mask[e] != 0.  Returns obs [N,...]."""
+        self._live()
         mptr = None
         if mask is not None:
             mask = torch.as_tensor(mask).to(self.device).to(torch.uint8).contiguous()
@@ -134,6 +140,8 @@ class VecEnv:
     def step(self, actions):
         """TetrisEnv.step (tetris_env.py:397-403) for N envs: (obs [N,...] f32, reward [N] f32, done [N] bool, info).
         The returned tensors are the env's own buffers and are overwritten by the next call."""
+        if self._closed:
+            self._live()
         a = self._actions(actions, (self.num_envs,))
         state, obs, reward, done, info = self._ptrs
         rc = self._st_step(self._cfg_ref, state, a.data_ptr(), obs, reward, done, info, self._aux_ref, self.num_envs,
@@ -145,6 +153,7 @@ class VecEnv:
     def step_many(self, actions, rollout_obs=False, rollout_info=False):
         """T steps in one launch.  actions [T, N].  Returns (obs, reward [T,N], done [T,N], info): obs is
         [T,N,...] if rollout_obs else the last step's [N,...]; same for info."""
+        self._live()
         T = int(actions.shape[0])
         a = self._actions(actions, (T, self.num_envs))
         n, dev = self.num_envs, self.device
@@ -159,7 +168,8 @@ class VecEnv:
             n * self.obs_elems if rollout_obs else 0, reward.data_ptr(), done.data_ptr(),
             info.data_ptr() if info is not None else None, n * ST_INFO_WORDS if rollout_info else 0,
             C.byref(self._aux_many()), n, self._stream()), "st_step_many")
-        return obs, reward, done, self._info(info)
+        # the terminal-observation buffer holds one step: step_many does not fill it, so it is not reported here
+        return obs, reward, done, self._info(info, terminal=False)
 
     def capture_step(self):
         """CUDA-graph the one-step launch: returns `GraphedStep`, whose call copies the
@@ -174,6 +184,7 @@ class VecEnv:
 
     def observe(self, draw_piece=True):
         """_observation(engine.render()) (tetris_env.py:317-321, 413-433) of the current state, no step."""
+        self._live()
         out = torch.empty_like(self.obs)
         self._check(self._L.st_observe(C.byref(self.cfg), self.state.data_ptr(), int(bool(draw_piece)),
                                        out.data_ptr(), self.num_envs, self._stream()), "st_observe")
@@ -181,18 +192,29 @@ class VecEnv:
 
     def render(self, size=160, draw_piece=True):
         """Batched TetrisEnv.render('rgb_array') (tetris_env.py:458-462): uint8 [N, size, size, 3]."""
+        self._live()
         out = torch.empty((self.num_envs, size, size, 3), dtype=torch.uint8, device=self.device)
         self._check(self._L.st_render(C.byref(self.cfg), self.state.data_ptr(), int(bool(draw_piece)), int(size),
                                       out.data_ptr(), self.num_envs, self._stream()), "st_render")
         return out
 
     def close(self):
-        self.state = self.obs = self.reward = self.done = self.info_buf = None
+        """TetrisEnv.close (tetris_env.py:466-467).  The cached raw device pointers go with the tensors: any later
+        step / reset / graph replay raises instead of launching onto memory the allocator has handed to someone else."""
+        if self._closed:
+            return
+        if self.state is not None and self.state.is_cuda:
+            torch.cuda.synchronize(self.device)
+        self._closed = True
+        self._ptrs = (None,) * 5
+        self._aux = self._aux_ref = self._info_views = None
+        self.state = self.obs = self.reward = self.done = self.info_buf = self.term_obs = self._queue = None
 
     # ---- piece source / state injection / diagnostics ----
     def set_piece_queue(self, queue):
         """queue [N, Q] of piece ids 0..6 (or None): the k-th piece of env e's lifetime becomes queue[e, k]
         instead of a draw of _choose_shape (tetris_env.py:183-191)."""
+        self._live()
         if queue is None:
             self._queue = None
             self._aux.piece_queue, self._aux.queue_len = None, 0
@@ -208,6 +230,7 @@ class VecEnv:
     def get_state(self):
         """(boards uint8 [N,W,H], scalars int32 [N,18]): id, rot, x, y, lock-delay counter, time, score,
         lines_cleared, holes, piece_height, deaths, shape_counts[7]."""
+        self._live()
         boards = torch.empty((self.num_envs, self.width, self.height), dtype=torch.uint8, device=self.device)
         scalars = torch.empty((self.num_envs, ST_UNPACKED_WORDS), dtype=torch.int32, device=self.device)
         self._check(self._L.st_get_state(C.byref(self.cfg), self.state.data_ptr(), boards.data_ptr(),
@@ -215,6 +238,7 @@ class VecEnv:
         return boards, scalars
 
     def set_state(self, boards=None, scalars=None):
+        self._live()
         b = s = None
         if boards is not None:
             b = torch.as_tensor(np.asarray(boards.cpu() if torch.is_tensor(boards) else boards)).to(torch.uint8)
@@ -277,6 +301,7 @@ class GraphedStep:
         torch.cuda.current_stream(env.device).wait_stream(side)
 
     def __call__(self, actions=None):
+        self.env._live()  # a replay after close() would write through pointers the allocator has recycled
         if actions is not None:
             self.actions.copy_(actions, non_blocking=True)
         self.graph.replay()

@@ -166,10 +166,23 @@ ST_API int st_host_set_piece_queue(StHostEnv *h, const uint8_t *queue, int32_t q
 ST_API int st_host_reset(StHostEnv *h, const uint8_t *mask, void *obs);
 ST_API int st_host_step(StHostEnv *h, const uint8_t *actions, void *obs, float *reward, uint8_t *done, int32_t *info);
 ST_API int st_host_observe(StHostEnv *h, int32_t draw_piece, void *obs);
+/* Pipelined TetrisEnv.step (ref:397-403) for callers that keep the link busy (the loop of README.md:43-51 with the
+ * next actions ready before the previous results are consumed, or two env groups stepped alternately):
+ * st_host_step_async copies `actions` [n] (any host memory, free again on return), enqueues the step and ONE
+ * device-to-host copy of its results into one of two page-locked slots owned by the handle, and returns without
+ * waiting; at most two steps may be in flight.  st_host_wait blocks until the OLDEST step in flight is in host
+ * memory and returns pointers into its slot: obs [n][st_obs_elems], reward [n], done [n], info [n][ST_INFO_WORDS]
+ * (any out-pointer may be NULL).  The pointers stay valid until the second st_host_step_async after this wait.
+ * The step kernel of call t+1 runs while the results of call t cross PCIe.  Synchronous st_host_* calls first
+ * drain (and discard) whatever is still in flight. */
+ST_API int st_host_step_async(StHostEnv *h, const uint8_t *actions);
+ST_API int st_host_wait(StHostEnv *h, const void **obs, const float **reward, const uint8_t **done,
+                        const int32_t **info);
 /* When a host buffer passed to st_host_step is page-locked (cudaHostAlloc / cudaHostRegister / torch
  * pin_memory), the kernel can read / write it in place over PCIe instead of staging through device memory.
  * mask = OR of ST_ZC_*; pageable buffers always take the staging path.  Default: everything in place when one
- * step's outputs are at most 8 MiB, staging copies (copy engine at link rate) above that. */
+ * step's outputs are at most 8 MiB, staging copies (copy engine at link rate) above that.  For the pipelined
+ * calls ST_ZC_OBS selects kernel writes straight into the page-locked slot instead of the copy engine. */
 #define ST_ZC_ACTIONS 1 /* kernel reads the actions from host memory */
 #define ST_ZC_SMALL 2   /* reward, done, info written straight to host memory */
 #define ST_ZC_OBS 4     /* observations written straight to host memory */

@@ -53,6 +53,7 @@ def lib():
         L.or_get_piece.argtypes = [C.c_void_p, C.c_void_p]
         L.or_set_piece.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.or_get_board.argtypes = [C.c_void_p, C.c_void_p]
+        L.or_render.argtypes = [C.c_void_p, C.c_void_p]
         L.or_set_board.argtypes = [C.c_void_p, C.c_void_p]
         L.or_get_counters.argtypes = [C.c_void_p, C.c_void_p]
         L.or_set_counters.argtypes = [C.c_void_p, C.c_void_p]
@@ -148,6 +149,27 @@ class OracleEnv:
         b = np.ascontiguousarray(b, dtype=np.float64)
         assert b.shape == (self.width, self.height)
         self._L.or_set_board(self._h, b.ctypes.data)
+
+    def render(self):
+        """TetrisEngine.render (tetris_env.py:317-321): the board with the active piece drawn."""
+        b = np.zeros((self.width, self.height), dtype=np.float64)
+        if self._L.or_render(self._h, b.ctypes.data) != 0:
+            raise TypeError("'NoneType' object is not iterable")  # shape is None before the first reset
+        return b
+
+    def __repr__(self):
+        """TetrisEngine.__repr__ (tetris_env.py:329-335)."""
+        state = self.render()
+        s = "o" + "-" * self.width + "o\n"
+        s += "\n".join(["|" + "".join(["X" if j else " " for j in i]) + "|" for i in state.T])
+        s += "\no" + "-" * self.width + "o"
+        return s
+
+    def human_frame(self, window_size=512):
+        """The array TetrisEnv.render('human') hands to pygame (tetris_env.py:444-447): the TRANSPOSED board through
+        convert_grayscale at window_size, then convert_grayscale_rgb."""
+        g = convert_grayscale(np.ascontiguousarray(self.render().T), window_size)
+        return np.repeat(g[:, :, None], 3, axis=2)
 
     def piece(self):
         """(id, rot, x, y, lock_delay_counter, piece_height)"""

@@ -466,6 +466,15 @@ API void or_set_piece(OrEnv *e, int id, int rot, int x, int y)
     for (int r = 0; r < (rot & 3); ++r) e->shape = rotated(e->shape, 0);
     e->ax = x; e->ay = y;
 }
+/* TetrisEngine.render (ref:317-321): _set_piece(True); copy; _set_piece(False).  -1 when there is no piece. */
+API int or_render(OrEnv *e, double *out)
+{
+    if (e->shape_id < 0) return -1;
+    set_piece(e, 1);
+    memcpy(out, e->board, sizeof(double) * e->W * e->H);
+    set_piece(e, 0);
+    return 0;
+}
 API void or_get_board(const OrEnv *e, double *out) { memcpy(out, e->board, sizeof(double) * e->W * e->H); }
 API void or_set_board(OrEnv *e, const double *in) { memcpy(e->board, in, sizeof(double) * e->W * e->H); }
 /* counters: time, score, lines, holes, piece_height, deaths, ld, counts[7] (14 ints) */

@@ -13,6 +13,8 @@ in place through oracle/ref_shim.py; nothing of it is copied.  Two fixtures:
                  observation bytes; plus the digest of every reset observation.
   render.npz     digests of `render('rgb_array')` (uint8 160x160x3, tetris_env.py:458-462) after reset and
                  after every step of short rollouts (`--render-only` regenerates just this file).
+  debug.npz      `repr(engine)` strings (tetris_env.py:329-335) and digests of the `render('human')` frames
+                 (tetris_env.py:437-457, pygame replaced by a recording stand-in); `--debug-only` regenerates it.
   scenarios.npz  injected-board known answers: the reward table of SURVEY.md
                  B.2 for every flag combination used there, lock-delay traces
                  (B.3) and the edge cases of B.4, each as (initial board,
@@ -216,11 +218,53 @@ def make_render():
     print("render cases:", len(meta))
 
 
+def make_debug():
+    """debug.npz: `repr(engine)` (tetris_env.py:329-335) and the frame of `render('human')` (tetris_env.py:437-457,
+    captured through a recording pygame stand-in) after reset and after every step of short rollouts."""
+    from _fake_pygame import make_fake_pygame
+
+    ref = load_reference()
+    out, meta = {}, {}
+    for name, kw in RENDER_CASES.items():
+        random.seed(11)
+        env = make_reference_env(**kw)
+        pieces = record_pieces(env)
+        actions = actions_for(61, 120)
+        fake = make_fake_pygame()
+        ref.pygame = fake
+        env.reset()
+        reprs, don = [repr(env.engine)], []
+        env.render(mode="human")
+        for a in actions:
+            _, _, d, _ = env.step(int(a))
+            don.append(bool(d))
+            if d:
+                env.reset()
+            reprs.append(repr(env.engine))
+            env.render(mode="human")
+        assert len(fake.frames) == len(actions) + 1 and fake.frames[0].shape == (512, 512, 3)
+        hd = [np.frombuffer(hashlib.sha256(np.ascontiguousarray(f, dtype=np.uint8).tobytes()).digest()[:8],
+                            dtype=np.uint64)[0] for f in fake.frames]
+        meta[name] = dict(kwargs=kw)
+        out[f"{name}/actions"] = actions
+        out[f"{name}/pieces"] = np.asarray(pieces, np.uint8)
+        out[f"{name}/done"] = np.asarray(don, np.uint8)
+        out[f"{name}/repr"] = np.frombuffer("\x00".join(reprs).encode(), dtype=np.uint8)
+        out[f"{name}/human_digest"] = np.asarray(hd, np.uint64)
+        out[f"{name}/human_first"] = np.ascontiguousarray(fake.frames[0], dtype=np.uint8)
+        out[f"{name}/calls"] = np.frombuffer(json.dumps([c if isinstance(c, str) else list(c) for c in fake.calls[:12]]).encode(), dtype=np.uint8)
+    out["__meta__"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, "debug.npz"), **out)
+    print("debug cases:", len(meta))
+
+
 def main():
     ref = load_reference()
     assert ref.shape_names == SHAPE_NAMES
     if "--render-only" in sys.argv:
         return make_render()
+    if "--debug-only" in sys.argv:
+        return make_debug()
     out = {}
     meta = {}
     for name, kw in CASES.items():
@@ -246,6 +290,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "scenarios.npz"), **out)
     print("scenarios:", len(meta))
     make_render()
+    make_debug()
 
 
 if __name__ == "__main__":

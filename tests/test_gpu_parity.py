@@ -584,3 +584,299 @@ def test_many_full_rows_at_once(st):
             assert got_info[e].tolist() == info_row(winfo), (W, H, e)
             assert np.array_equal(obs[e].cpu().numpy(), want), (W, H, e)
             assert np.array_equal(got_boards[e], o.board.astype(np.uint8)), (W, H, e)
+
+
+# ---- round-2 additions: instantiations and sizes the first suite did not reach ---------------------------------
+@pytest.mark.parametrize("n,kw", [
+    (8192, dict(reward_step=True, advanced_clears=True)),
+    (20000, dict(penalise_height_increase=True, penalise_holes_increase=True, lock_delay=3, step_reset=True)),
+    (30000, dict(width=20, height=40, penalise_holes=True)),
+    (12289, dict(width=28, height=24, high_scoring=True)),   # 64-bit row registers, ragged
+    (40000, dict(width=26, height=40, lock_delay=1)),        # 64-bit rows, two rows per lane
+])
+def test_midsize_ram_batches_match_oracle(st, n, kw):
+    """Mid-size ram batches under `auto` run the loop-free warp-per-env build (st_main_kernel<..., MANY=false>,
+    6145..24575 envs, ..65535 when H > 31), which neither the small (MANY=true) nor the large (thread-per-env) tests
+    touch.  Every env, every step: reward / done / info; observations of the last step."""
+    from oracle.oracle import rollout
+
+    T = 48
+    acts = np.random.RandomState(n).choice(7, size=(T, n), p=[0.12, 0.12, 0.28, 0.12, 0.12, 0.12, 0.12]).astype(np.uint8)
+    env = st.VecEnv(n, device="cuda:0", seed=77, env_id_base=3, **kw)
+    env.reset()
+    a_dev = torch.from_numpy(acts).cuda()
+    rew, don, inf = [], [], []
+    for t in range(T):
+        obs, r, d, info = env.step(a_dev[t])
+        rew.append(r.clone()); don.append(d.clone()); inf.append(env.info_buf[:, INFO13].clone())
+    want = rollout(n, acts, seed=77, env_id_base=3, want_info=True, **kw)
+    assert want["error"] == 0 and env.poll_errors() == 0
+    assert np.array_equal(torch.stack(rew).cpu().numpy(), want["reward"])
+    assert np.array_equal(torch.stack(don).cpu().numpy().astype(np.uint8), want["done"])
+    assert np.array_equal(torch.stack(inf).cpu().numpy(), want["info"])
+    assert np.array_equal(obs.reshape(n, -1).cpu().numpy(), want["obs"])
+    assert want["done"].sum() > 0
+
+
+@pytest.mark.parametrize("kw", [dict(obs_type="grayscale", extend_dims=True, high_scoring=True), dict(obs_type="rgb"),
+                                dict(obs_type="rgb", width=6, height=12, lock_delay=1),
+                                dict(obs_type="grayscale", width=20, height=40)])
+def test_step_many_equals_repeated_step_images(st, kw):
+    """st_step_many in the image modes (st_main_kernel<*, 1|2, STEP, *, MANY=true>): a [T, N, ...] rollout buffer
+    written by one launch equals T single-step launches, observation by observation."""
+    n, T = 37, 8
+    rs = np.random.RandomState(17)
+    for rounds in range(3):  # the third round starts from well-filled boards
+        acts = rs.choice(7, size=(T, n), p=[0.1, 0.1, 0.4, 0.1, 0.1, 0.1, 0.1]).astype(np.uint8)
+        if rounds == 0:
+            a = st.VecEnv(n, device="cuda:0", seed=5, **kw)
+            b = st.VecEnv(n, device="cuda:0", seed=5, **kw)
+            a.reset(), b.reset()
+        obs_t, rew_t, don_t, inf_t = [], [], [], []
+        for t in range(T):
+            o, r, d, _ = a.step(torch.from_numpy(acts[t]).cuda())
+            obs_t.append(o.clone()); rew_t.append(r.clone()); don_t.append(d.clone()); inf_t.append(a.info_buf.clone())
+        obs, rew, don, info = b.step_many(torch.from_numpy(acts).cuda(), rollout_obs=True, rollout_info=True)
+        assert obs.shape == (T,) + tuple(a.obs.shape)
+        assert torch.equal(obs, torch.stack(obs_t))
+        assert torch.equal(rew, torch.stack(rew_t)) and torch.equal(don, torch.stack(don_t))
+        assert torch.equal(info["time"], torch.stack(inf_t)[:, :, 2])
+        assert torch.equal(info["statistics"], torch.stack(inf_t)[:, :, 8:15])
+        assert torch.equal(a.state, b.state)
+        assert "terminal_observation" not in info
+    # obs_t_stride = 0: every step overwrites the same buffer, the last one remains
+    acts = rs.randint(0, 7, (T, n)).astype(np.uint8)
+    for t in range(T):
+        o, _, _, _ = a.step(torch.from_numpy(acts[t]).cuda())
+    o2, _, _, _ = b.step_many(torch.from_numpy(acts).cuda())
+    assert torch.equal(o, o2)
+
+
+@pytest.mark.parametrize("n,kw,T", [
+    (262144, dict(obs_type="grayscale", extend_dims=True, high_scoring=True), 10),  # C4: 7.4 GB of observations
+    (131072, dict(obs_type="rgb"), 8),                                              # C5a per-GPU share: 11.1 GB
+])
+def test_baseline_size_images_match_oracle(st, n, kw, T, ram_path):
+    """BASELINE.json C4 / C5a at full size on one GPU: observation offsets cross 4 GiB.  Envs at both ends, at CTA
+    boundaries and in the middle are replayed through the oracle and compared byte for byte at the last step, plus
+    the size-independent census over ALL envs."""
+    from oracle.oracle import OracleEnv
+
+    if ram_path != "auto":
+        pytest.skip("image modes have one kernel; run once")
+    torch.cuda.empty_cache()
+    free, _ = torch.cuda.mem_get_info()
+    if free < n * 84 * 84 * (3 if kw["obs_type"] == "rgb" else 1) * 4 * 1.25:
+        pytest.skip("not enough free device memory for the full-size observation buffer")
+    env = st.VecEnv(n, device="cuda:0", seed=11, **kw)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    sample = [0, 1, 7, 8, 9, n // 2 - 1, n // 2, n // 2 + 5, n - 9, n - 8, n - 1]
+    idx = torch.tensor(sample, device="cuda")
+    acts, rews, dones = [], [], []
+    for t in range(T):
+        a = torch.randint(0, 7, (n,), dtype=torch.uint8, device="cuda", generator=g)
+        a[idx[::2]] = 2  # some sampled envs hard-drop every step: locks, spawns and episode ends within T steps
+        obs, r, d, info = env.step(a)
+        acts.append(a[idx].cpu().numpy()); rews.append(r[idx].cpu().numpy().copy()); dones.append(d[idx].cpu().numpy().copy())
+    got = obs[idx].cpu().numpy()
+    for k, e in enumerate(sample):
+        o = OracleEnv(seed=11, env_id=e, **kw)
+        o.reset()
+        for t in range(T):
+            want, rr, dd, _ = o.step(int(acts[t][k]))
+            assert rews[t][k] == rr and bool(dones[t][k]) == dd, (e, t)
+            if dd:
+                want = o.reset()
+        assert np.array_equal(got[k], want), e
+    # census over every env, in chunks (a full-size boolean temporary would not fit beside the 11 GB buffer)
+    ch = 3 if kw["obs_type"] == "rgb" else 1
+    ram = st.VecEnv(n, device="cuda:0", seed=11, **{**kw, "obs_type": "ram", "extend_dims": False})
+    ram.state.copy_(env.state)
+    cells = ram.observe(True).sum(dim=(1, 2))
+    cells[d] = 0
+    flat = obs.reshape(n, -1)
+    for lo in range(0, n, 8192):
+        f = flat[lo:lo + 8192]
+        assert bool(((f == 0) | (f == 128) | (f == 190)).all())
+        assert torch.equal((f == 190).sum(1).float(), cells[lo:lo + 8192] * 9 * ch)
+        assert bool(((f == 0).sum(1) == 3735 * ch).all())
+
+
+def test_v26_api_matches_oracle(st):
+    """TetrisEnvV26 (reset(seed=...) -> (obs, info), 5-tuple step) against the oracle keyed with the same seed."""
+    from oracle.oracle import OracleEnv
+
+    kw = dict(width=6, height=10, reward_step=True, penalise_holes_increase=True)
+    env = st.TetrisEnvV26(**kw)
+    obs, info = env.reset(seed=5)
+    o = OracleEnv(seed=5, env_id=0, **kw)
+    wobs, winfo = o.reset(return_info=True)
+    assert np.array_equal(obs, wobs) and info == winfo
+    rs = np.random.RandomState(2)
+    episodes = 0
+    for a in rs.choice(7, size=300, p=[0.1, 0.1, 0.4, 0.1, 0.1, 0.1, 0.1]):
+        obs, r, term, trunc, info = env.step(int(a))
+        wobs, wr, wd, winfo = o.step(int(a))
+        assert trunc is False and term == wd and r == wr and info == winfo
+        assert np.array_equal(obs, wobs)
+        if term:
+            episodes += 1
+            obs, info = env.reset()
+            wobs, winfo = o.reset(return_info=True)
+            assert np.array_equal(obs, wobs) and info == winfo
+    assert episodes >= 3
+    env.close()
+
+
+DBG = golden("debug.npz")
+
+
+@pytest.mark.parametrize("key", DBG.keys())
+def test_repr_and_human_render_match_reference_fixture(st, key):
+    """`repr(env.engine)` (tetris_env.py:329-335) byte for byte, and the frame `render('human')`
+    (tetris_env.py:437-457) hands to pygame, against fixtures generated from the reference (pygame is replaced by
+    the same recording stand-in on both sides)."""
+    import sys
+
+    from _fake_pygame import make_fake_pygame
+
+    g = lambda f: DBG.get(key, f)
+    want_repr = bytes(g("repr")).decode().split("\x00")
+    fake = make_fake_pygame()
+    saved = sys.modules.get("pygame")
+    sys.modules["pygame"] = fake
+    try:
+        env = st.make("SimpleTetris-v0", **DBG.kwargs(key))
+        env.engine.set_pieces(g("pieces"))
+        with pytest.raises(TypeError):
+            repr(env.engine)  # no piece before the first reset (ref:170-172)
+        env.reset()
+        assert repr(env.engine) == want_repr[0]
+        assert env.render(mode="human") is None
+        assert np.array_equal(fake.frames[0], g("human_first"))
+        for t, a in enumerate(g("actions")):
+            _, _, d, _ = env.step(int(a))
+            assert d == bool(g("done")[t])
+            if d:
+                env.reset()
+            assert repr(env.engine) == want_repr[t + 1], (key, t)
+            env.render(mode="human")
+            assert digest_u8(fake.frames[-1]) == g("human_digest")[t + 1], (key, t)
+        calls = [c if isinstance(c, str) else list(c) for c in fake.calls[:12]]
+        assert calls == __import__("json").loads(bytes(g("calls")).decode())
+        env.close()
+    finally:
+        if saved is None:
+            sys.modules.pop("pygame", None)
+        else:
+            sys.modules["pygame"] = saved
+
+
+def test_render_human_without_pygame_raises_importerror(st):
+    import importlib.util
+
+    if importlib.util.find_spec("pygame") is not None:
+        pytest.skip("pygame installed")
+    env = st.make("SimpleTetris-v0")
+    env.reset()
+    with pytest.raises(ImportError):
+        env.render(mode="human")
+    assert env.render(mode="rgb_array").shape == (160, 160, 3)
+
+
+def test_closed_env_raises(st):
+    env = st.VecEnv(64, device="cuda:0")
+    env.reset()
+    g = env.capture_step()
+    a = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    env.step(a), g(a)
+    env.close()
+    for call in (lambda: env.step(a), lambda: env.reset(), lambda: env.step_many(a[None]), lambda: g(a),
+                 lambda: env.observe(), lambda: env.get_state()):
+        with pytest.raises(RuntimeError):
+            call()
+    env.close()  # idempotent
+
+
+def test_step_many_rejects_misaligned_strides(st):
+    env = st.VecEnv(5, width=3, height=5, device="cuda:0")  # 15 floats per env: 75 floats per step is not 16-byte aligned
+    env.reset()
+    acts = torch.zeros((4, 5), dtype=torch.uint8, device="cuda")
+    with pytest.raises(RuntimeError, match="obs_t_stride"):
+        env.step_many(acts, rollout_obs=True)
+    env.step_many(acts)  # stride 0 is fine
+    env4 = st.VecEnv(8, width=3, height=5, device="cuda:0")  # 120 floats per step: aligned
+    env4.reset()
+    o, _, _, _ = env4.step_many(torch.zeros((4, 8), dtype=torch.uint8, device="cuda"), rollout_obs=True)
+    assert o.shape == (4, 8, 3, 5)
+
+
+def test_current_device_is_left_alone(st):
+    """Every ABI call runs on cfg->device and restores the caller's device (torch may switch devices between calls)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from oracle.oracle import rollout
+
+    kw = dict(reward_step=True, advanced_clears=True)
+    n, T = 300, 40
+    acts = np.random.RandomState(4).randint(0, 7, (T, n)).astype(np.uint8)
+    torch.cuda.set_device(1)
+    env = st.VecEnv(n, device="cuda:0", seed=9, **kw)
+    assert torch.cuda.current_device() == 1
+    env.reset()
+    junk = torch.ones(1024, device="cuda:1")
+    rew = []
+    for t in range(T):
+        torch.cuda.set_device(t % 2)
+        a = torch.from_numpy(acts[t]).to("cuda:0")
+        obs, r, d, _ = env.step(a)
+        assert torch.cuda.current_device() == t % 2
+        junk += 1  # unrelated work on the other device
+        rew.append(r.cpu().numpy().copy())
+    want = rollout(n, acts, seed=9, **kw)
+    assert np.array_equal(np.stack(rew), want["reward"])
+    assert np.array_equal(obs.reshape(n, -1).cpu().numpy(), want["obs"])
+    single = st.make("SimpleTetris-v0", device=0)
+    single.reset(), single.step(2)
+    assert torch.cuda.current_device() == (T - 1) % 2
+    torch.cuda.set_device(0)
+
+
+# ---- pipelined host path (st_host_step_async / st_host_wait) ------------------------------------------------
+@pytest.mark.parametrize("kw,n,zc", [
+    (dict(reward_step=True, advanced_clears=True), 500, None), (dict(reward_step=True, advanced_clears=True), 500, 0),
+    (dict(width=6, height=12, lock_delay=1), 77, 7), (dict(obs_type="grayscale", width=7, height=9), 21, 0),
+    (dict(obs_type="rgb"), 16, None),
+])
+def test_host_pipeline_matches_sync_and_oracle(st, kw, n, zc):
+    """HostVecEnv.step_async / step_wait with two steps in flight == the synchronous step == the oracle."""
+    from oracle.oracle import rollout
+
+    T = 60
+    acts = np.random.RandomState(8).choice(7, size=(T, n), p=[0.1, 0.1, 0.4, 0.1, 0.1, 0.1, 0.1]).astype(np.uint8)
+    want = rollout(n, acts, seed=4, want_info=True, **kw)
+    sync = st.HostVecEnv(n, seed=4, zero_copy=zc, **kw)
+    pipe = st.HostVecEnv(n, seed=4, zero_copy=zc, **kw)
+    assert not sync.reset().any() or kw.get("obs_type", "ram") != "ram"
+    pipe.reset()
+    got = []
+    pipe.step_async(acts[0])
+    for t in range(T):
+        if t + 1 < T:
+            pipe.step_async(acts[t + 1])  # two in flight
+        o, r, d, info = pipe.step_wait()
+        so, sr, sd, sinfo = sync.step(acts[t])
+        assert np.array_equal(o, so) and np.array_equal(r, sr) and np.array_equal(d, sd), t
+        assert np.array_equal(info["statistics"], sinfo["statistics"]) and np.array_equal(info["time"], sinfo["time"])
+        assert np.array_equal(r, want["reward"][t]) and np.array_equal(d.astype(np.uint8), want["done"][t]), t
+        got.append(o.copy())
+    assert np.array_equal(got[-1].reshape(n, -1), want["obs"])
+    with pytest.raises(RuntimeError):
+        pipe.step_wait()  # nothing in flight
+    pipe.step_async(acts[0]), pipe.step_async(acts[1])
+    with pytest.raises(RuntimeError):
+        pipe.step_async(acts[2])  # a third would overwrite a slot nobody has read
+    pipe.reset()  # drains and discards
+    assert pipe.poll_errors() == 0 and sync.poll_errors() == 0
+    pipe.close(), sync.close()

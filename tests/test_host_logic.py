@@ -55,3 +55,57 @@ def test_package_surface():
     assert st.TetrisEnv.metadata == {"render.modes": ["human", "rgb_array"], "render_fps": 8}  # tetris_env.py:339
     with pytest.raises(KeyError):
         st.make("CartPole-v1")
+
+
+def test_gym_registration_path():
+    """gym_simpletetris/__init__.py:3-6: `register(id='SimpleTetris-v0', entry_point=...)` — run against stand-in
+    `gym` / `gymnasium` registration modules (neither package is installed in this image)."""
+    import importlib
+    import sys
+    import types
+
+    calls = []
+
+    def fake(modname, version):
+        top = types.ModuleType(modname)
+        top.__version__ = version
+        envs = types.ModuleType(modname + ".envs")
+        reg = types.ModuleType(modname + ".envs.registration")
+        reg.register = lambda id, entry_point, **kw: calls.append((modname, id, entry_point))  # noqa: A002
+        top.envs, envs.registration = envs, reg
+        return {modname: top, modname + ".envs": envs, modname + ".envs.registration": reg}
+
+    saved = {k: sys.modules.get(k) for k in ("gym", "gym.envs", "gym.envs.registration", "gymnasium", "gymnasium.envs",
+                                             "gymnasium.envs.registration")}
+    try:
+        sys.modules.update(fake("gym", "0.21.0"))
+        sys.modules.update(fake("gymnasium", "0.29.1"))
+        st._register()
+        assert ("gym", "SimpleTetris-v0", "gym_simpletetris_b200.envs:TetrisEnv") in calls  # 4-tuple API for gym <= 0.25
+        assert ("gymnasium", "SimpleTetris-v0", "gym_simpletetris_b200.envs:TetrisEnvV26") in calls
+        calls.clear()
+        sys.modules.update(fake("gym", "0.26.2"))
+        st._register()
+        assert ("gym", "SimpleTetris-v0", "gym_simpletetris_b200.envs:TetrisEnvV26") in calls
+        # the entry point strings resolve to the classes
+        for _, _, entry in calls:
+            mod, cls = entry.split(":")
+            assert getattr(importlib.import_module(mod), cls) in (st.TetrisEnv, st.TetrisEnvV26)
+        # a registry that refuses (id already registered) must not break the import
+        sys.modules["gym.envs.registration"].register = lambda **kw: (_ for _ in ()).throw(RuntimeError("dup"))
+        st._register()
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def test_host_vec_env_has_no_cpu_path():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        st.HostVecEnv(8)

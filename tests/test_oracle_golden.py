@@ -69,3 +69,30 @@ def test_survey_b4_five_I():
     assert g("done").tolist()[:7] == [0, 0, 0, 0, 1, 1, 1]
     assert g("reward").tolist()[4:7] == [-100, -100, -100]
     assert g("info")[4:7, 5].tolist() == [1, 2, 3]  # deaths
+
+
+DBG = golden("debug.npz")
+
+
+def u8_digest(a):
+    import hashlib
+
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a, dtype=np.uint8).tobytes()).digest()[:8], dtype=np.uint64)[0]
+
+
+@pytest.mark.parametrize("key", DBG.keys())
+def test_repr_and_human_frame_match_reference(key):
+    """tetris_env.py:329-335 (`__repr__`) and :437-457 (`render('human')` frame) after reset and after every step."""
+    g = lambda f: DBG.get(key, f)
+    want_repr = bytes(g("repr")).decode().split("\x00")
+    env = OracleEnv(pieces=g("pieces"), **DBG.kwargs(key))
+    env.reset()
+    assert repr(env) == want_repr[0]
+    assert np.array_equal(env.human_frame(), g("human_first"))
+    for t, a in enumerate(g("actions")):
+        _, _, d, _ = env.step(int(a))
+        assert d == bool(g("done")[t])
+        if d:
+            env.reset()
+        assert repr(env) == want_repr[t + 1], (key, t)
+        assert u8_digest(env.human_frame()) == g("human_digest")[t + 1], (key, t)

@@ -167,10 +167,14 @@ int st_step_many(const StConfig *cfg, void *state, const uint8_t *actions, int32
     if (n && (!state || !actions || !reward || !done)) return fail(ST_E_INVALID, "state/actions/reward/done is NULL%s");
     if (T < 1) return fail(ST_E_INVALID, "T < 1%s");
     if (((uintptr_t)state | (uintptr_t)obs) & 15) return fail(ST_E_INVALID, "state and obs must be 16-byte aligned%s");
-    if (T > 1) {  // every step's observation block must keep the 16-byte alignment the vector / bulk stores rely on
+    if (T > 1) {  // every step's observation block must keep the alignment the vector / bulk stores rely on:
+        // 16 bytes for images (TMA bulk stores), four elements for ram boards with H % 4 == 0 (one store per four
+        // cells), one element otherwise (scalar stores)
         const int64_t esz = cfg->obs_u8 ? 1 : 4;
-        if (obs && obs_t_stride != 0 && (obs_t_stride < p.obs_elems * n || (obs_t_stride * esz) % 16 != 0))
-            return fail(ST_E_INVALID, "obs_t_stride must be 0 or >= n*st_obs_elems, with obs_t_stride*elem_size a multiple of 16%s");
+        const int64_t align = cfg->obs_type != ST_OBS_RAM ? 16 : (cfg->height % 4 == 0 ? 4 * esz : esz);
+        if (obs && obs_t_stride != 0 && (obs_t_stride < p.obs_elems * n || (obs_t_stride * esz) % align != 0))
+            return fail(ST_E_INVALID, "obs_t_stride must be 0 or >= n*st_obs_elems, and keep every step's block aligned "
+                                      "(16 bytes for images, 4 elements for ram boards with height % 4 == 0)%s");
         if (info && info_t_stride != 0 && (info_t_stride < n * ST_INFO_WORDS || info_t_stride % ST_INFO_WORDS != 0))
             return fail(ST_E_INVALID, "info_t_stride must be 0 or a multiple of ST_INFO_WORDS >= n*ST_INFO_WORDS%s");
         if (aux && aux->terminal_obs)

@@ -1,14 +1,17 @@
 """TEST INFRASTRUCTURE ONLY — loader for the UNMODIFIED reference file.
 
-Loads `/root/reference/gym_simpletetris/envs/tetris_env.py` by path under an
-import shim (the reference imports `gym`, `gym.spaces` and `pygame`, none of
-which exist in this image, and uses the removed alias `np.float` at
-tetris_env.py:140).  Nothing is copied: the file is executed where it lies.
+Loads `gym_simpletetris/envs/tetris_env.py` by path under an import shim (the
+reference imports `gym`, `gym.spaces` and `pygame`, none of which exist in
+this image, and uses the removed alias `np.float` at tetris_env.py:140).
+The file is executed where it lies: `/root/reference/...` in the build
+container, else the pip install of the unmodified reference under
+`baseline/_ref/` (git-ignored; made by `__graft_entry__.build()`, it travels
+to the GPU box so that `bench.py` can time the reference's own Python path
+there).  No reference source is part of this repository.
 
-Only `tests/golden/make_golden.py` and the `not gpu` tests that pin the C
-oracle (`oracle/st_oracle.c`) use this module, and only in the build
-container: `/root/reference` does not exist on the GPU box, where
-`reference_available()` is False and those tests skip.
+Users: `tests/golden/make_golden.py`, the `not gpu` tests that pin the C
+oracle (`oracle/st_oracle.c`), and `bench.py`'s CPU legs
+(`oracle/ref_python_bench.py`).  `-m gpu` tests never load it.
 """
 from __future__ import annotations
 
@@ -18,13 +21,25 @@ import sys
 import types
 import warnings
 
-REFERENCE_FILE = "/root/reference/gym_simpletetris/envs/tetris_env.py"
+_CANDIDATES = (
+    "/root/reference/gym_simpletetris/envs/tetris_env.py",
+    os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "gym_simpletetris",
+                 "envs", "tetris_env.py"),
+)
+
+
+def REFERENCE_FILE() -> str:
+    """Path of the unmodified reference file that will be executed ('' if there is none)."""
+    for p in _CANDIDATES:
+        if os.path.isfile(p):
+            return p
+    return ""
 
 _module = None
 
 
 def reference_available() -> bool:
-    return os.path.isfile(REFERENCE_FILE)
+    return bool(REFERENCE_FILE())
 
 
 class _Env:  # stand-in for gym.Env (tetris_env.py:338)
@@ -50,7 +65,7 @@ def load_reference():
     if _module is not None:
         return _module
     if not reference_available():
-        raise FileNotFoundError(REFERENCE_FILE)
+        raise FileNotFoundError(_CANDIDATES[0])
     import numpy as np
 
     if not hasattr(np, "float"):
@@ -65,7 +80,7 @@ def load_reference():
     pygame = types.ModuleType("pygame")
     sys.modules.update({"gym": gym, "gym.spaces": spaces, "pygame": pygame})
     try:
-        spec = importlib.util.spec_from_file_location("_ref_tetris_env", REFERENCE_FILE)
+        spec = importlib.util.spec_from_file_location("_ref_tetris_env", REFERENCE_FILE())
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
     finally:

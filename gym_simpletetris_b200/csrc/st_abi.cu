@@ -32,7 +32,8 @@ bool config_ok(const StConfig *c)
            c->obs_type >= ST_OBS_RAM && c->obs_type <= ST_OBS_RGB && c->device >= 0;
 }
 
-int row_bytes(const StConfig *c) { return c->width <= 16 ? 2 : 4; }
+// 32-bit words per board column of the env record: bit y of column x = cell (x, y)
+int col_words(const StConfig *c) { return c->height <= 31 ? 1 : 2; }
 
 // Fills everything of Params that derives from StConfig; buffers are left zero.
 int make_params(const StConfig *c, const StAux *aux, int64_t n, st::Params *out)
@@ -54,7 +55,7 @@ int make_params(const StConfig *c, const StAux *aux, int64_t n, st::Params *out)
     p.pen_holes = c->penalise_holes != 0;
     p.pen_holes_inc = c->penalise_holes_increase != 0;
     p.fullmask = c->width == 32 ? 0xffffffffu : ((1u << c->width) - 1u);
-    p.row_bytes = row_bytes(c);
+    p.col_words = col_words(c);
     p.stride = (int)st_state_stride(c);
     p.seed_lo = (uint32_t)c->seed;
     p.seed_hi = (uint32_t)(c->seed >> 32);
@@ -121,8 +122,7 @@ extern "C" {
 int64_t st_state_stride(const StConfig *cfg)
 {
     if (!config_ok(cfg)) return -1;
-    const int64_t b = 4 * ST_STATE_WORDS + (int64_t)cfg->height * row_bytes(cfg);
-    return (b + 3) & ~(int64_t)3;
+    return 4 * ST_STATE_WORDS + (int64_t)cfg->width * 4 * col_words(cfg);
 }
 
 int64_t st_obs_elems(const StConfig *cfg)
@@ -609,7 +609,7 @@ int st_host_step_async(StHostEnv *h, const uint8_t *actions)
     // the slot's device block is still being read by the D2H copy of the step before last
     if (h->head >= 2) HCHECK(cudaStreamWaitEvent(h->stream, sl.copied, 0), "cudaStreamWaitEvent");
     HCHECK(cudaMemcpyAsync(sl.act_dev, sl.act_host, n, cudaMemcpyHostToDevice, h->stream), "H2D actions");
-    const bool zc = (h->zero_copy & ST_ZC_OBS) && sl.host_alias;
+    const bool zc = (h->zero_copy & ST_ZC_PIPELINED) && sl.host_alias;
     unsigned char *blk = zc ? (unsigned char *)sl.host_alias : sl.dev;
     StAux aux = host_aux(h);
     if (int rc = st_step(&h->cfg, h->state, sl.act_dev, blk, (float *)(blk + h->off_reward), blk + h->off_done,

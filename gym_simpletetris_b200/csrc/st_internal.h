@@ -23,7 +23,7 @@ struct Params {
     int step_reset, auto_reset;
     int reward_step, pen_height, pen_height_inc, adv_clears, high_scoring, pen_holes, pen_holes_inc;
     uint32_t fullmask;
-    int row_bytes;  // 2 (W<=16) or 4
+    int col_words;  // 32-bit words per board column in the env record: 1 (H <= 31) or 2
     int stride;     // bytes per env record
     uint32_t seed_lo, seed_hi;
     long long env_id_base;

@@ -800,16 +800,37 @@ def test_closed_env_raises(st):
 
 
 def test_step_many_rejects_misaligned_strides(st):
-    env = st.VecEnv(5, width=3, height=5, device="cuda:0")  # 15 floats per env: 75 floats per step is not 16-byte aligned
-    env.reset()
-    acts = torch.zeros((4, 5), dtype=torch.uint8, device="cuda")
-    with pytest.raises(RuntimeError, match="obs_t_stride"):
-        env.step_many(acts, rollout_obs=True)
-    env.step_many(acts)  # stride 0 is fine
-    env4 = st.VecEnv(8, width=3, height=5, device="cuda:0")  # 120 floats per step: aligned
+    """The per-step observation block must keep the alignment of the stores that write it: four elements for ram
+    boards with height % 4 == 0 (one 16-byte store per four cells), one element otherwise (scalar stores)."""
+    import ctypes as C
+
+    from gym_simpletetris_b200 import native
+    L = native.lib()
+    T = 4
+    env = st.VecEnv(5, width=3, height=5, device="cuda:0", seed=2)  # 15 floats per env, scalar stores: any stride works
+    ref = st.VecEnv(5, width=3, height=5, device="cuda:0", seed=2)
+    env.reset(), ref.reset()
+    acts = torch.from_numpy(np.random.RandomState(1).randint(0, 7, (T, 5)).astype(np.uint8)).cuda()
+    o, r, _, _ = env.step_many(acts, rollout_obs=True)  # 75 floats per step: not a multiple of 16 bytes, and fine
+    for t in range(T):
+        ot, rt, _, _ = ref.step(acts[t])
+        assert torch.equal(o[t], ot) and torch.equal(r[t], rt)
+    env4 = st.VecEnv(8, width=3, height=8, device="cuda:0")  # height % 4 == 0: vector stores
     env4.reset()
-    o, _, _, _ = env4.step_many(torch.zeros((4, 8), dtype=torch.uint8, device="cuda"), rollout_obs=True)
-    assert o.shape == (4, 8, 3, 5)
+    n, el = 8, env4.obs_elems
+    buf = torch.zeros(T * (n * el + 4), dtype=torch.float32, device="cuda")
+    rew = torch.zeros((T, n), dtype=torch.float32, device="cuda")
+    don = torch.zeros((T, n), dtype=torch.uint8, device="cuda")
+    a4 = torch.zeros((T, n), dtype=torch.uint8, device="cuda")
+
+    def call(stride):
+        return L.st_step_many(C.byref(env4.cfg), env4.state.data_ptr(), a4.data_ptr(), T, buf.data_ptr(), stride,
+                              rew.data_ptr(), don.data_ptr(), None, 0, C.byref(env4._aux_many()), n, env4._stream())
+    assert call(n * el + 1) != 0 and b"obs_t_stride" in L.st_last_error()   # breaks the 16-byte alignment
+    assert call(n * el - 4) != 0 and b"obs_t_stride" in L.st_last_error()   # steps would overlap
+    assert call(n * el + 4) == 0 and call(n * el) == 0 and call(0) == 0
+    o, _, _, _ = env4.step_many(a4, rollout_obs=True)
+    assert o.shape == (T, 8, 3, 8)
 
 
 def test_current_device_is_left_alone(st):
@@ -846,7 +867,7 @@ def test_current_device_is_left_alone(st):
 # ---- pipelined host path (st_host_step_async / st_host_wait) ------------------------------------------------
 @pytest.mark.parametrize("kw,n,zc", [
     (dict(reward_step=True, advanced_clears=True), 500, None), (dict(reward_step=True, advanced_clears=True), 500, 0),
-    (dict(width=6, height=12, lock_delay=1), 77, 7), (dict(obs_type="grayscale", width=7, height=9), 21, 0),
+    (dict(width=6, height=12, lock_delay=1), 77, 15), (dict(obs_type="grayscale", width=7, height=9), 21, 0),
     (dict(obs_type="rgb"), 16, None),
 ])
 def test_host_pipeline_matches_sync_and_oracle(st, kw, n, zc):

@@ -242,6 +242,42 @@ __device__ __forceinline__ void piece_on_rows(RowT (&pm)[RPL], const PieceRows<R
     }
 }
 
+// Env records keep the board as COLUMN words (bit y of column x = cell (x, y); st_kernels_tpe.cuh works on them
+// directly).  This kernel wants one ROW per lane: lane x holds column x, every lane gathers its row's bit of each
+// column with one shuffle per column, and the other way round with one ballot per column.  Column bits at y >= H
+// are zero, so lanes beyond the board come out as bare walls.
+template <int RPL, typename RowT>
+__device__ __forceinline__ void rows_from_columns(RowT (&row)[RPL], uint32_t clo, uint32_t chi, int W, int lane, RowT walls)
+{
+    RowT r0 = 0, r1 = 0;
+#pragma unroll 4
+    for (int x = 0; x < W; ++x) {
+        const uint32_t c = __shfl_sync(FULL, clo, x);
+        r0 |= (RowT)((c >> lane) & 1u) << x;
+        if (RPL == 2) {
+            const uint32_t d = __shfl_sync(FULL, chi, x);
+            r1 |= (RowT)((d >> lane) & 1u) << x;
+        }
+    }
+    row[0] = (r0 << OFF) | walls;
+    if (RPL == 2) row[RPL - 1] = (r1 << OFF) | walls;
+}
+
+template <int RPL, typename RowT>
+__device__ __forceinline__ void columns_from_rows(const RowT (&row)[RPL], uint32_t &clo, uint32_t &chi, int W, int lane)
+{
+    clo = 0; chi = 0;
+#pragma unroll 4
+    for (int x = 0; x < W; ++x) {
+        const uint32_t b0 = __ballot_sync(FULL, ((row[0] >> (x + OFF)) & 1) != 0);
+        if (lane == x) clo = b0;
+        if (RPL == 2) {
+            const uint32_t b1 = __ballot_sync(FULL, ((row[RPL - 1] >> (x + OFF)) & 1) != 0);
+            if (lane == x) chi = b1;
+        }
+    }
+}
+
 struct Piece {
     int id, rot, x, y;
 };
@@ -491,7 +527,6 @@ __global__ void __launch_bounds__(32 * Wpc<OBS>::value, OBS == 0 ? ST_RAM_MINBLO
     // Programmatic dependent launch: let the next step's grid start its prologue while this one runs ...
     asm volatile("griddepcontrol.launch_dependents;");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int H = p.H;
     const int n = (int)p.n;
     const int e = blockIdx.x * WPC + warp;  // this warp's env (launch_main keeps n below 2^31)
     const bool valid = e < n;
@@ -525,20 +560,16 @@ __global__ void __launch_bounds__(32 * Wpc<OBS>::value, OBS == 0 ? ST_RAM_MINBLO
     RowT row[RPL], disp[RPL], row_in[RPL];
     int sw = 0, errbits = 0;
     Piece pc = {7, 0, 0, 0};
+    uint32_t clo = 0, chi = 0;  // lane x < W: column x of the env record (bit y = cell (x, y)); chi = rows 32..63
     if (selected) {
         if (lane < kStateWords) sw = rec_w[lane];
-#pragma unroll
-        for (int k = 0; k < RPL; ++k) {
-            const int Y = lane + 32 * k;
-            uint32_t v = 0;
-            if (Y < H) v = p.row_bytes == 2 ? (uint32_t)reinterpret_cast<const uint16_t *>(rec_w + kStateWords)[Y]
-                                            : reinterpret_cast<const uint32_t *>(rec_w + kStateWords)[Y];
-            row[k] = ((RowT)v << OFF) | walls;
+        const uint32_t *cols = reinterpret_cast<const uint32_t *>(rec_w + kStateWords);
+        if (lane < p.W) {
+            if (RPL == 1) clo = cols[lane];
+            else { clo = cols[2 * lane]; chi = cols[2 * lane + 1]; }
         }
-    } else {
-#pragma unroll
-        for (int k = 0; k < RPL; ++k) row[k] = walls;
     }
+    rows_from_columns<RPL, RowT>(row, clo, chi, p.W, lane, walls);
     // running output pointers (advance per step in st_step_many)
     const uint8_t *act_p = MODE == MODE_STEP ? p.actions + e : nullptr;
     float *rew_p = MODE == MODE_STEP ? p.reward + e : nullptr;
@@ -719,14 +750,11 @@ __global__ void __launch_bounds__(32 * Wpc<OBS>::value, OBS == 0 ? ST_RAM_MINBLO
 #pragma unroll
         for (int k = 0; k < RPL; ++k) dirty |= row[k] != row_in[k];
         if (__any_sync(FULL, dirty)) {
-#pragma unroll
-            for (int k = 0; k < RPL; ++k) {
-                const int Y = lane + 32 * k;
-                const uint32_t v = (uint32_t)(row[k] >> OFF) & p.fullmask;
-                if (Y < H) {
-                    if (p.row_bytes == 2) reinterpret_cast<uint16_t *>(rec_w + kStateWords)[Y] = (uint16_t)v;
-                    else reinterpret_cast<uint32_t *>(rec_w + kStateWords)[Y] = v;
-                }
+            columns_from_rows<RPL, RowT>(row, clo, chi, p.W, lane);
+            uint32_t *cols = reinterpret_cast<uint32_t *>(rec_w + kStateWords);
+            if (lane < p.W) {
+                if (RPL == 1) cols[lane] = clo;
+                else { cols[2 * lane] = clo; cols[2 * lane + 1] = chi; }
             }
         }
     }
@@ -760,10 +788,10 @@ __global__ void st_get_state_kernel(const __grid_constant__ Params p, uint8_t *b
         for (int i = 1; i < kStateWords; ++i) s[3 + i] = w[i];
     }
     if (boards) {
-        for (int y = 0; y < p.H; ++y) {
-            const uint32_t r = p.row_bytes == 2 ? (uint32_t)reinterpret_cast<const uint16_t *>(rec + 60)[y]
-                                                : reinterpret_cast<const uint32_t *>(rec + 60)[y];
-            for (int x = 0; x < p.W; ++x) boards[(e * p.W + x) * p.H + y] = (r >> x) & 1u;
+        const uint32_t *cols = reinterpret_cast<const uint32_t *>(rec + 4 * kStateWords);
+        for (int x = 0; x < p.W; ++x) {
+            const unsigned long long c = p.col_words == 1 ? cols[x] : (cols[2 * x] | ((unsigned long long)cols[2 * x + 1] << 32));
+            for (int y = 0; y < p.H; ++y) boards[(e * p.W + x) * p.H + y] = (uint8_t)((c >> y) & 1ull);
         }
     }
 }
@@ -785,11 +813,12 @@ __global__ void st_set_state_kernel(const __grid_constant__ Params p, const uint
         for (int i = 1; i < kStateWords; ++i) w[i] = s[3 + i];
     }
     if (boards) {
-        for (int y = 0; y < p.H; ++y) {
-            uint32_t r = 0;
-            for (int x = 0; x < p.W; ++x) r |= (boards[(e * p.W + x) * p.H + y] ? 1u : 0u) << x;
-            if (p.row_bytes == 2) reinterpret_cast<uint16_t *>(rec + 60)[y] = (uint16_t)r;
-            else reinterpret_cast<uint32_t *>(rec + 60)[y] = r;
+        uint32_t *cols = reinterpret_cast<uint32_t *>(rec + 4 * kStateWords);
+        for (int x = 0; x < p.W; ++x) {
+            unsigned long long c = 0;
+            for (int y = 0; y < p.H; ++y) c |= (boards[(e * p.W + x) * p.H + y] ? 1ull : 0ull) << y;
+            if (p.col_words == 1) cols[x] = (uint32_t)c;
+            else { cols[2 * x] = (uint32_t)c; cols[2 * x + 1] = (uint32_t)(c >> 32); }
         }
     }
 }
@@ -820,8 +849,11 @@ __global__ void __launch_bounds__(256) st_render_kernel(const __grid_constant__ 
         const int Y = threadIdx.x;
         uint32_t v = 0;
         if (Y < p.H) {
-            v = p.row_bytes == 2 ? (uint32_t)reinterpret_cast<const uint16_t *>(rec + 60)[Y]
-                                 : reinterpret_cast<const uint32_t *>(rec + 60)[Y];
+            const uint32_t *cols = reinterpret_cast<const uint32_t *>(rec + 4 * kStateWords);
+            for (int x = 0; x < p.W; ++x) {
+                const uint32_t c = p.col_words == 1 ? cols[x] : cols[2 * x + (Y >> 5)];
+                v |= ((c >> (Y & 31)) & 1u) << x;
+            }
             const Piece pc = unpack_piece(*reinterpret_cast<const int *>(rec));
             if (p.draw_piece && pc.id < 7) {  // _set_piece(True) (ref:323-327): in-board cells only
                 const PieceRows<unsigned long long> pr = piece_rows<unsigned long long>(pc.id, pc.rot, pc.x);

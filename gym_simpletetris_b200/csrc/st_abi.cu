@@ -75,6 +75,8 @@ int make_params(const StConfig *c, const StAux *aux, int64_t n, st::Params *out)
     p.pad_left = (size - p.inner_h) / 2;
     p.inv_h20 = ((1u << 20) + c->height - 1) / c->height;
     p.inv_sw20 = ((1u << 20) + (p.stride >> 2) - 1) / (p.stride >> 2);
+    p.inv_nq32 = (c->height % 4 == 0) ? (uint32_t)(((1ull << 32) + c->width * c->height / 4 - 1) / (c->width * c->height / 4)) : 0;
+    p.inv_w20 = ((1u << 20) + c->width - 1) / c->width;
     p.inv_hq20 = (c->height % 4 == 0) ? ((1u << 20) + c->height / 4 - 1) / (c->height / 4) : 0;
     if (aux) {
         p.queue = aux->piece_queue;

@@ -33,6 +33,8 @@ struct Params {
     uint32_t inv_h20;   // ceil(2^20 / H)      : i / H      for i < 2048
     uint32_t inv_hq20;  // ceil(2^20 / (H/4))  : q / (H/4)  when H % 4 == 0
     uint32_t inv_sw20;  // ceil(2^20 / (stride/4)) : word index -> record, thread-per-env kernel
+    uint32_t inv_nq32;  // ceil(2^32 / (W*H/4)) : float4 slot of a group's block -> env, thread-per-env kernel
+    uint32_t inv_w20;   // ceil(2^20 / W)      : (env, column) item -> env, thread-per-env kernel
     // buffers
     unsigned char *state;
     const uint8_t *actions;
@@ -52,7 +54,9 @@ struct Params {
     long long obs_t_stride, info_t_stride;
     int mode;
     int draw_piece;
-    int tpe_epw;  // thread-per-env kernel: envs per warp
+    int tpe_epw;     // thread-per-env kernel: envs per group (one group = one warp pass)
+    int tpe_l2;      // thread-per-env kernel: L2 eviction hints (bit 0: outputs evict_first, bit 1: records evict_last)
+    int tpe_staged;  // thread-per-env kernel: observations through a shared-memory block + TMA bulk store
 };
 
 cudaError_t launch_main(const Params &p, int obs_type, cudaStream_t stream);

@@ -1,10 +1,13 @@
-// K1b — thread-per-env ram step on COLUMN bitboards (included by st_kernels.cu).
+// K1b — thread-per-env ram step on COLUMN bitboards, observations staged in shared memory and sent out with TMA
+// bulk stores (included by st_kernels.cu).
 //
 // The warp-per-env kernel (K1) spends ~400 warp-instructions per env-step: ideal for small batches, where the
 // machine is latency-bound and a whole warp per env keeps every rare branch uniform, but issue-bound from
-// ~16k envs up.  Here one THREAD steps one env and the warp does the memory work cooperatively:
-//   1. the warp copies its env records (contiguous in HBM) into shared memory with 16-byte loads; the record
-//      pitch in smem is odd, so lane r touching word c of ITS record is conflict-free;
+// ~16k envs up.  Here one THREAD steps one env and the warp does the memory work cooperatively, for one GROUP of
+// `epw` consecutive envs at a time (a warp walks over several groups when the grid is capped):
+//   1. the group's env records (contiguous in HBM) arrive in shared memory through cp.async (LDGSTS), the next
+//      group's records are already in flight while this one is stepped; the record pitch in smem is odd, so lane r
+//      touching word c of ITS record is conflict-free;
 //   2. each lane runs TetrisEngine.step (ref:243-304) on its record in smem.  The record holds the board as one
 //      word per COLUMN (bit y of column x = cell (x, y)), which is what makes the per-thread engine short:
 //        * a piece is four cells (i, j); the collision answer for EVERY anchor height at once is the OR over the
@@ -15,22 +18,50 @@
 //          a cleared row is squeezed out of every column with three logic ops;
 //   3. info / reward / done go out coalesced, auto-reset envs are cleared, every other lane ORs its piece
 //      into its smem columns (the reference's _set_piece(True), ref:301);
-//   4. the warp expands all its boards into float32 [W][H] — the observation is column-major like the record, four
-//      cells are four adjacent bits of one word — with 16-byte stores, 512 contiguous bytes per warp instruction;
+//   4. the warp expands the group's boards into float32 [W][H] — the observation is column-major like the record:
+//      one lane per (env, column), four cells = four adjacent bits = one 16-byte table entry — into a warp-private
+//      staging block in shared memory, and ONE cp.async.bulk (TMA) store sends the block (the group's
+//      observations are contiguous in HBM) on its way; the warp does not wait for it: the block is only
+//      needed again after the next group's records were stepped;
 //   5. lanes erase their piece again (ref:303) and the records are stored back, coalesced.
 #pragma once
 
 namespace st {
 
-#ifndef ST_TPE_WARPS
-#define ST_TPE_WARPS 4
+#ifndef ST_TPE_MINBLOCKS
+#define ST_TPE_MINBLOCKS 4  // 256-thread CTAs x 4 = 64 registers per thread: 32 resident warps per SM
 #endif
-constexpr int kTpeWarps = ST_TPE_WARPS;
+constexpr int kTpeMaxWarps = 8;  // warps per CTA is a launch-time choice (1, 2, 4 or 8)
 
-// Piece cells for the thread-per-env engine: entry = four cells, byte c = (i + 3) | (j + 3) << 3 (ref:10-19, rotated
-// as ref:22-26), then maxj + 3 in bits 32..35.
+// Phase timestamps of every warp (profiling builds only: -DST_TPE_TRACE=1, tools/tpe_trace.py)
+#ifndef ST_TPE_TRACE
+#define ST_TPE_TRACE 0
+#endif
+#if ST_TPE_TRACE
+__device__ unsigned long long *g_tpe_trace = nullptr;  // [8 launches][kTraceWarps][16]
+constexpr size_t kTraceWarps = 1 << 15;
+__device__ __forceinline__ unsigned long long tpe_now()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define TPE_MARK(slot)                                                                                        \
+    do {                                                                                                      \
+        if (g_tpe_trace && lane == 0 && g == (long long)blockIdx.x * wpc + warp)                              \
+            g_tpe_trace[((size_t)(p.draw_piece & 7) * kTraceWarps + (size_t)blockIdx.x * wpc + warp) * 16 + (slot)] = tpe_now(); \
+    } while (0)
+#else
+#define TPE_MARK(slot) do { } while (0)
+#endif
+
+// Piece tables for the thread-per-env engine (ref:10-19, rotated as ref:22-26).
+//   e[s]: the four cells, byte c = (i + 3) | (j + 3) << 3, then maxj + 3 in bits 32..35          (collision test)
+//   c[s]: the same piece by COLUMN, four 10-bit fields = (i + 3) | pattern << 3, bit j + 3 of the pattern = cell
+//         (i, j); unused fields are 0                                                              (drawing the piece)
 struct CellTab {
     unsigned long long e[28];
+    unsigned long long c[28];
 };
 
 constexpr CellTab make_cell_tab()
@@ -57,6 +88,15 @@ constexpr CellTab make_cell_tab()
             }
             m |= (unsigned long long)(mx + 3) << 32;
             t.e[id * 4 + r] = m;
+            unsigned long long cols = 0;
+            int nf = 0;
+            for (int i = -3; i <= 3; ++i) {
+                unsigned pat = 0;
+                for (int k = 0; k < 4; ++k)
+                    if (c[k][0] == i) pat |= 1u << (c[k][1] + 3);
+                if (pat) cols |= (unsigned long long)((unsigned)(i + 3) | (pat << 3)) << (10 * nf++);
+            }
+            t.c[id * 4 + r] = cols;
             for (int k = 0; k < 4; ++k) { int i = c[k][0], j = c[k][1]; c[k][0] = j; c[k][1] = -i; }
         }
     }
@@ -70,11 +110,17 @@ template <> struct ColOps<uint32_t> {
     static constexpr int kWords = 1;
     static __device__ __forceinline__ int popc(uint32_t v) { return __popc(v); }
     static __device__ __forceinline__ int ffs(uint32_t v) { return __ffs((int)v); }
+    // column v moved by j = s3 - 3 rows: bit y' of the result = bit y' + j of v (bits shifted in are clear)
+    static __device__ __forceinline__ uint32_t by_rows(uint32_t v, int s3) { return (uint32_t)(((unsigned long long)v << 3) >> s3); }
 };
 template <> struct ColOps<unsigned long long> {
     static constexpr int kWords = 2;
     static __device__ __forceinline__ int popc(unsigned long long v) { return __popcll(v); }
     static __device__ __forceinline__ int ffs(unsigned long long v) { return __ffsll((long long)v); }
+    static __device__ __forceinline__ unsigned long long by_rows(unsigned long long v, int s3)
+    {
+        return s3 >= 3 ? (v >> (s3 - 3)) : (v << (3 - s3));
+    }
 };
 
 // One env record in shared memory: 15 scalar words, then W column words (two 32-bit halves when H > 31).
@@ -98,9 +144,41 @@ struct TpeRec {
 };
 
 struct Cells {
-    int i[4], j[4];
+    int i[4];   // column offset of cell k
+    int s3[4];  // row offset + 3
     int maxj;
 };
+
+// The piece at anchor (x, y), column by column: up to four board columns X[c] (-1 = none / outside the board) and
+// the piece's cells in that column as a mask of board rows (rows above the board and below the floor drop out, which
+// is _set_piece's `0 <= y < height` test, ref:325-326).
+template <typename ColT>
+struct PieceCols {
+    int X[4];
+    ColT m[4];
+};
+
+template <typename ColT>
+__device__ __forceinline__ PieceCols<ColT> tpe_piece_cols(const unsigned long long *s_cols, int id, int rot, int x, int y, int W, int H)
+{
+    const unsigned long long e = s_cols[id * 4 + rot];
+    const ColT hmask = (((ColT)1 << H) - 1);
+    PieceCols<ColT> pc;
+    constexpr int kYMax = sizeof(ColT) == 4 ? 56 : 66;  // an injected anchor far below the floor: every cell drops
+    y = y > kYMax ? kYMax : y;                          // out, no shift overflows
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const uint32_t f = (uint32_t)(e >> (10 * c)) & 1023u;
+        const int X = x + (int)(f & 7u) - 3;
+        const uint32_t pat = f >> 3;
+        ColT m;
+        if constexpr (sizeof(ColT) == 4) m = (ColT)(((unsigned long long)pat << y) >> 3);
+        else m = y >= 3 ? ((ColT)pat << (y - 3)) : ((ColT)pat >> (3 - y));  // shift <= 63
+        pc.m[c] = m & hmask;
+        pc.X[c] = (pat != 0u && (unsigned)X < (unsigned)W) ? X : -1;
+    }
+    return pc;
+}
 
 __device__ __forceinline__ Cells tpe_cells(const unsigned long long *s_cells, int id, int rot)
 {
@@ -110,7 +188,7 @@ __device__ __forceinline__ Cells tpe_cells(const unsigned long long *s_cells, in
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         c.i[k] = (int)((lo >> (8 * k)) & 7u) - 3;
-        c.j[k] = (int)((lo >> (8 * k + 3)) & 7u) - 3;
+        c.s3[k] = (int)((lo >> (8 * k + 3)) & 7u);
     }
     c.maxj = (int)((uint32_t)(e >> 32) & 15u) - 3;
     return c;
@@ -125,9 +203,9 @@ __device__ __forceinline__ ColT tpe_collisions(const TpeRec<ColT> &rec, const Ce
     for (int k = 0; k < 4; ++k) {
         const int X = x + c.i[k];
         const ColT v = (unsigned)X < (unsigned)W ? rec.col(X) : ~(ColT)0;  // outside the board: ref:34
-        // cell row = y' + j: the anchors it blocks are the column shifted by j; for j < 0 the low -j anchors put the
-        // cell above the board, where nothing is tested (ref:32-33) — the left shift leaves exactly those bits clear
-        cm |= c.j[k] >= 0 ? (v >> c.j[k]) : (v << -c.j[k]);
+        // cell row = y' + j: the anchors it blocks are the column moved by j rows; for j < 0 the low -j anchors put
+        // the cell above the board, where nothing is tested (ref:32-33) — the shift leaves exactly those bits clear
+        cm |= ColOps<ColT>::by_rows(v, c.s3[k]);
     }
     int fl = H - c.maxj;  // anchors whose lowest cell is at or below the floor (ref:34 `y >= board.shape[1]`)
     fl = fl < 0 ? 0 : fl;
@@ -137,7 +215,7 @@ __device__ __forceinline__ ColT tpe_collisions(const TpeRec<ColT> &rec, const Ce
 
 // _new_piece / _choose_shape (ref:183-200) on the record's shape_counts (words 8..14).
 template <typename ColT>
-__device__ __forceinline__ int tpe_spawn(const TpeRec<ColT> &rec, const Params &p, int e, int &errbits)
+__device__ __forceinline__ int tpe_spawn(const TpeRec<ColT> &rec, const Params &p, long long e, int &errbits)
 {
     int c[7];
     int total = 0, mx = 0;
@@ -168,34 +246,49 @@ __device__ __forceinline__ int tpe_spawn(const TpeRec<ColT> &rec, const Params &
     return id;
 }
 
-// The lock branch (ref:262-299).
+// Over all columns: the rows every column has (full), the rows any column has, and _count_holes (ref:218-220: per
+// column, the empty cells below its top-most filled one = H - top - popc; an empty column finds the sentinel bit H).
 template <typename ColT>
-__device__ __forceinline__ void tpe_lock(const TpeRec<ColT> &rec, Piece &pc, const Cells &cl, const Params &p, int e,
-                                         int &reward, int &done, int &errbits)
+__device__ __forceinline__ void tpe_scan(const TpeRec<ColT> &rec, int W, int H, ColT &full, ColT &any, int &holes)
 {
     using Ops = ColOps<ColT>;
-    const int H = p.H, W = p.W;
-    const ColT hmask = ~(ColT)0 >> (8 * (int)sizeof(ColT) - H);
+    const ColT hbit = (ColT)1 << H;
+    full = hbit - 1;
+    any = 0;
+    int sf = 0, sp = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {  // _set_piece(True) (ref:263): in-board cells only
-        const int X = pc.x + cl.i[k], Y = pc.y + cl.j[k];
-        if (Y >= 0 && Y < H && (unsigned)X < (unsigned)W) rec.set_col(X, rec.col(X) | ((ColT)1 << Y));
-    }
-    // One pass over the columns answers _clear_lines' can_clear (ref:206: a row is full when every column has it),
-    // _count_holes (ref:218-220: per column, the empty cells below its top-most filled one = H - top - popc) and
-    // sum(np.any(board, axis=0)) (ref:287,289: rows with any cell = popc of the OR of all columns).
-    ColT full = hmask, any = 0;
-    int holes = 0;
     for (int x = 0; x < W; ++x) {
         const ColT c = rec.col(x);
         full &= c;
         any |= c;
-        holes += c ? H + 1 - Ops::ffs(c) - Ops::popc(c) : 0;
+        sf += Ops::ffs(c | hbit);
+        sp += Ops::popc(c);
     }
+    holes = W * (H + 1) - sf - sp;
+}
+
+// The lock branch (ref:262-299).
+template <typename ColT>
+__device__ __forceinline__ void tpe_lock(const TpeRec<ColT> &rec, Piece &pc, const unsigned long long *s_cells, const Params &p,
+                                         int W, int H, long long e, int &reward, int &done, int &errbits)
+{
+    using Ops = ColOps<ColT>;
+    {   // _set_piece(True) (ref:263): in-board cells only
+        const PieceCols<ColT> q = tpe_piece_cols<ColT>(s_cells + 28, pc.id, pc.rot, pc.x, pc.y, W, H);
+        ColT v[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] = q.X[c] >= 0 ? rec.col(q.X[c]) : 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (q.X[c] >= 0) rec.set_col(q.X[c], v[c] | q.m[c]);
+    }
+    // One pass over the columns answers _clear_lines' can_clear (ref:206: a row is full when every column has it),
+    // _count_holes and sum(np.any(board, axis=0)) (ref:287,289: rows with any cell = popc of the OR of all columns).
+    ColT full, any;
+    int holes;
+    tpe_scan(rec, W, H, full, any, holes);
     const int k = Ops::popc(full);
     if (k) {  // rare: squeeze the full rows out of every column, top-most first (ref:207-214), then recount
-        any = 0;
-        holes = 0;
         for (int x = 0; x < W; ++x) {
             ColT c = rec.col(x);
             ColT f = full;
@@ -205,9 +298,9 @@ __device__ __forceinline__ void tpe_lock(const TpeRec<ColT> &rec, Piece &pc, con
                 c = (c & ~(bit | (bit - 1))) | ((c & (bit - 1)) << 1);  // rows below r stay, rows above move down by one
             }
             rec.set_col(x, c);
-            any |= c;
-            holes += c ? H + 1 - Ops::ffs(c) - Ops::popc(c) : 0;
         }
+        ColT dummy;
+        tpe_scan(rec, W, H, dummy, any, holes);
         rec.w[4] += (uint32_t)k;
     }
     const int nonempty = Ops::popc(any);
@@ -247,10 +340,9 @@ __device__ __forceinline__ void tpe_lock(const TpeRec<ColT> &rec, Piece &pc, con
 
 // TetrisEngine.step (ref:243-304) up to, not including, the composition of the returned state.
 template <typename ColT>
-__device__ __forceinline__ void tpe_engine_step(const TpeRec<ColT> &rec, int action, const Params &p, int e,
+__device__ __forceinline__ void tpe_engine_step(const TpeRec<ColT> &rec, int action, const Params &p, int W, int H, long long e,
                                                 const unsigned long long *s_cells, int &reward, int &done, int &errbits)
 {
-    const int H = p.H, W = p.W;
     Piece pc = unpack_piece((int)rec.w[0]);
     reward = p.reward_step;
     done = 0;
@@ -285,89 +377,139 @@ __device__ __forceinline__ void tpe_engine_step(const TpeRec<ColT> &rec, int act
     rec.w[2] += 1u;  // time (ref:253)
     if ((cm >> (y + 1)) & 1) {                           // _has_dropped (ref:202-203)
         ld += 1;
-        if (ld >= p.lock_mod) ld %= p.lock_mod;
-        if (ld == 0) tpe_lock(rec, pc, cl, p, e, reward, done, errbits);
+        if (ld >= p.lock_mod) {                          // ref:258 `% (lock_delay + 1)`: one subtraction unless a
+            ld -= p.lock_mod;                            // counter beyond the modulus was injected
+            if (ld >= p.lock_mod) ld %= p.lock_mod;
+        }
+        if (ld == 0) tpe_lock(rec, pc, s_cells, p, W, H, e, reward, done, errbits);
     }
     rec.w[1] = (uint32_t)ld;
     rec.w[0] = (uint32_t)pack_piece(pc);
 }
 
-template <typename ColT>
-__global__ void __launch_bounds__(32 * kTpeWarps) st_step_tpe_kernel(const __grid_constant__ Params p)
+__device__ __forceinline__ uint32_t smem_u32(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+
+// L2 eviction priorities (Params::tpe_l2 bit 0: observations / info are write-once streams -> evict_first;
+// bit 1: env records are re-read by the next step -> evict_last)
+__device__ __forceinline__ unsigned long long l2_policy(int kind)  // 0 normal, 1 evict_first, 2 evict_last
 {
-    extern __shared__ __align__(16) uint32_t s_dyn[];
-    __shared__ unsigned long long s_cells[28];
-    constexpr int CW = ColOps<ColT>::kWords;
-    asm volatile("griddepcontrol.launch_dependents;");
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x < 28) s_cells[threadIdx.x] = c_cells.e[threadIdx.x];
-    const int H = p.H, W = p.W;
-    const int SW = p.stride >> 2;  // words per record in HBM
-    const int pitch = SW | 1;      // odd pitch in smem: lane r, word c -> bank (r * pitch + c) % 32, conflict-free
-    const int epw = p.tpe_epw;     // envs per warp (32, 16, 8 or 4): fewer envs per warp = more warps for mid-size batches
-    uint32_t *recs = s_dyn + warp * epw * pitch;
-    const long long e0 = ((long long)blockIdx.x * kTpeWarps + warp) * epw;
-    int nvalid = (int)(p.n - e0 < epw ? p.n - e0 : epw);
-    nvalid = nvalid < 0 ? 0 : nvalid;
-    __syncthreads();  // s_cells
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (nvalid == 0) return;
+    unsigned long long pol;
+    if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void stg128(void *ptr, const float4 &v, unsigned long long pol)
+{
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol));
+}
+__device__ __forceinline__ void stg128(void *ptr, const uint4 &v, unsigned long long pol)
+{
+    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol));
+}
+__device__ __forceinline__ void stg32(void *ptr, uint32_t v, unsigned long long pol)
+{
+    asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(ptr), "r"(v), "l"(pol));
+}
 
-    // the action bytes are issued first so that their miss overlaps the record copy
-    const int e = (int)e0 + lane;
-    unsigned int action_u = 6u;
-    if (lane < nvalid) asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(action_u) : "l"(p.actions + e));
-
-    // 1. records HBM -> smem
-    uint32_t *g_rec = reinterpret_cast<uint32_t *>(p.state + e0 * (long long)p.stride);
-    const int nwords = nvalid * SW;
-    const bool vec_ok = pitch == SW && ((e0 * (long long)p.stride) & 15) == 0;  // contiguous in both, 16-byte aligned
-    if (vec_ok) {
-        const int nvec = nwords >> 2;
-        for (int i = lane; i < nvec; i += 32) reinterpret_cast<uint4 *>(recs)[i] = reinterpret_cast<const uint4 *>(g_rec)[i];
-        for (int i = (nvec << 2) + lane; i < nwords; i += 32) recs[i] = g_rec[i];
-    } else {
-        for (int i = lane; i < nwords; i += 32) {
-            const int r = (int)(((uint32_t)i * p.inv_sw20) >> 20);
-            recs[r * pitch + (i - r * SW)] = g_rec[i];
+// Records of one group: HBM -> shared memory, asynchronously (one cp.async group per call, possibly empty).
+__device__ __forceinline__ void tpe_fetch(uint32_t *recs, const unsigned char *state, long long e0, int nvalid, int SW, int pitch,
+                                          int stride, uint32_t inv_sw20, int lane, unsigned long long pol)
+{
+    if (nvalid > 0) {
+        const uint32_t *g_rec = reinterpret_cast<const uint32_t *>(state + e0 * (long long)stride);
+        const int nwords = nvalid * SW;
+        if (pitch == SW && (reinterpret_cast<uintptr_t>(g_rec) & 15) == 0) {  // contiguous in both, 16-byte aligned
+            const int nvec = nwords >> 2;
+            for (int i = lane; i < nvec; i += 32)
+                asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(recs + 4 * i)), "l"(g_rec + 4 * i), "l"(pol) : "memory");
+            for (int i = (nvec << 2) + lane; i < nwords; i += 32)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(recs + i)), "l"(g_rec + i) : "memory");
+        } else {
+            for (int i = lane; i < nwords; i += 32) {
+                const int r = (int)(((uint32_t)i * inv_sw20) >> 20);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(recs + r * pitch + (i - r * SW))), "l"(g_rec + i) : "memory");
+            }
         }
     }
-    __syncwarp();
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
 
-    const TpeRec<ColT> rec = {recs + lane * pitch};
+// WCT / HCT: board size known at compile time (0 = taken from Params): the column loops unroll and the divisions by
+// W, H / 4 fold into constants for the boards every BASELINE.json workload uses.
+template <typename ColT, int WCT, int HCT>
+__global__ void __launch_bounds__(32 * kTpeMaxWarps, ST_TPE_MINBLOCKS) st_step_tpe_kernel(const __grid_constant__ Params p)
+{
+    extern __shared__ __align__(128) uint32_t s_dyn[];
+    __shared__ unsigned long long s_cells[56];  // CellTab: e[28], then c[28]
+    __shared__ __align__(16) float4 s_lut[16];  // four cells -> four float32 (ref:400)
+    constexpr int CW = ColOps<ColT>::kWords;
+    asm volatile("griddepcontrol.launch_dependents;");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+#if ST_TPE_TRACE
+    if (g_tpe_trace && lane == 0)
+        g_tpe_trace[((size_t)(p.draw_piece & 7) * kTraceWarps + (size_t)blockIdx.x * wpc + warp) * 16 + 9] = tpe_now();
+#endif
+    for (int i = threadIdx.x; i < 56; i += blockDim.x) s_cells[i] = i < 28 ? c_cells.e[i] : c_cells.c[i - 28];
+    if (threadIdx.x < 16)
+        s_lut[threadIdx.x] = make_float4((threadIdx.x & 1) ? 1.0f : 0.0f, (threadIdx.x & 2) ? 1.0f : 0.0f,
+                                         (threadIdx.x & 4) ? 1.0f : 0.0f, (threadIdx.x & 8) ? 1.0f : 0.0f);
+    const int H = HCT ? HCT : p.H, W = WCT ? WCT : p.W;
+    const int SW = (WCT ? kStateWords + WCT * CW : p.stride >> 2);  // words per record in HBM
+    const int pitch = SW | 1;      // odd pitch in smem: lane r, word c -> bank (r * pitch + c) % 32, conflict-free
+    const int epw = p.tpe_epw;     // envs per group (32, 16, 8 or 4): fewer envs per warp = more warps for mid-size batches
+    const bool u8 = p.obs_u8 != 0;
+    const int nel = W * H;
+    // warp-private shared memory: two record buffers (this group, next group), then the observation staging block
+    const int rec_words = (epw * pitch + 3) & ~3;
+    const bool staged = p.tpe_staged != 0;
+    const int stage_words = staged ? (epw * nel * (u8 ? 1 : 4) + 15) >> 4 << 2 : 0;
+    uint32_t *const wbase = s_dyn + (size_t)warp * (2 * rec_words + stage_words);
+    unsigned char *const stage = reinterpret_cast<unsigned char *>(wbase + 2 * rec_words);
+    const long long ngroups = (p.n + epw - 1) / epw;
+    const long long gstride = (long long)gridDim.x * wpc;
+    long long g = (long long)blockIdx.x * wpc + warp;
+    __syncthreads();  // s_cells, s_lut
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (g >= ngroups) return;
+    TPE_MARK(0);
+
     int errbits = 0;
     const size_t n_envs = (size_t)p.n;
+    const unsigned long long pol_out = l2_policy((p.tpe_l2 & 1) ? 1 : 0), pol_state = l2_policy((p.tpe_l2 & 2) ? 2 : 0);
+    {
+        const long long e0 = g * epw;
+        const int nv = (int)(p.n - e0 < epw ? p.n - e0 : epw);
+        tpe_fetch(wbase, p.state, e0, nv, SW, pitch, p.stride, p.inv_sw20, lane, pol_state);
+    }
+    int cur = 0;
+    for (; g < ngroups; g += gstride, cur ^= 1) {
+    uint32_t *const recs = wbase + cur * rec_words;
+    const long long e0 = g * epw;
+    const int nvalid = (int)(p.n - e0 < epw ? p.n - e0 : epw);
+    const long long e = e0 + lane;
+    unsigned int action_u = 6u;  // issued before the wait so that its miss overlaps the record copy
+    if (lane < nvalid) asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(action_u) : "l"(p.actions + e));
+    {   // 1. next group's records on their way; this group's have arrived
+        const long long gn = g + gstride;
+        const long long en = gn * epw;
+        const int nvn = gn < ngroups ? (int)(p.n - en < epw ? p.n - en : epw) : 0;
+        tpe_fetch(wbase + (cur ^ 1) * rec_words, p.state, en, nvn, SW, pitch, p.stride, p.inv_sw20, lane, pol_state);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+    }
+    __syncwarp();
+    TPE_MARK(1);
+
+    const TpeRec<ColT> rec = {recs + lane * pitch};
     for (int t = 0; t < p.T; ++t) {  // st_step_many: the records stay in shared memory between steps
     // 2. engine, one env per lane
     int reward = 0, done = 0;
-    if (lane < nvalid) tpe_engine_step(rec, (int)action_u, p, e, s_cells, reward, done, errbits);
+    if (lane < nvalid) tpe_engine_step(rec, (int)action_u, p, W, H, e, s_cells, reward, done, errbits);
     if (t + 1 < p.T && lane < nvalid)  // next step's action, in flight during the cooperative phases
         asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(action_u) : "l"(p.actions + (size_t)(t + 1) * n_envs + e));
     __syncwarp();
+    TPE_MARK(2);
 
-    // 3. info (pre-reset), reward, done; then auto-reset or piece overlay
-    if (p.info) {
-        int32_t *g_info = p.info + (long long)t * p.info_t_stride + e0 * kStateWords;
-        for (int j = lane; j < nvalid * kStateWords; j += 32) {
-            const int r = (j * 4370) >> 16;  // j / 15 for j < 480
-            const int c = j - r * kStateWords;
-            const uint32_t v = recs[r * pitch + c];
-            g_info[j] = c == 0 ? (int32_t)(v & 15u) : (int32_t)v;
-        }
-    }
-    if (lane < nvalid) {
-        p.reward[(size_t)t * n_envs + e] = (float)reward;
-        p.done[(size_t)t * n_envs + e] = (unsigned char)done;
-        if (done && p.stats) {
-            atomicAdd(p.stats, 1ull);
-            atomicAdd(p.stats + 1, (unsigned long long)(long long)(int)rec.w[2]);
-            atomicAdd(p.stats + 2, (unsigned long long)(long long)(int)rec.w[4]);
-            atomicAdd(p.stats + 3, (unsigned long long)(long long)(int)rec.w[3]);
-        }
-    }
-    __syncwarp();
-    const bool u8 = p.obs_u8 != 0;
-    const int nel = W * H;
     if (p.term_obs) {  // terminal observation of the envs that end here: their board already holds the locked piece
         unsigned term = __ballot_sync(FULL, lane < nvalid && done && p.auto_reset);
         char *tb = reinterpret_cast<char *>(p.term_obs) + ((long long)t * p.obs_t_stride + e0 * (long long)p.obs_elems) * (u8 ? 1 : 4);
@@ -386,104 +528,259 @@ __global__ void __launch_bounds__(32 * kTpeWarps) st_step_tpe_kernel(const __gri
         }
         __syncwarp();
     }
-    int pX[4] = {-1, -1, -1, -1}, pY[4] = {0, 0, 0, 0};  // the piece's in-board cells (column, row); -1 = none
+    // 3. what the observation shows: an auto-reset env shows the empty board of clear() (ref:306-315), every other
+    //    lane ORs its piece into its columns (_set_piece(True), ref:301).  The observation goes out FIRST (it is 80 % of
+    //    the bytes and the store pipe is what the kernel waits for); info is read before the reset touches the counters.
+    const bool resets = lane < nvalid && done && p.auto_reset;
+    // Few values stay live across the observation loop (its stores want registers of their own): the piece's
+    // column masks and the four column numbers packed into one word (0xff = none).
+    ColT shown_m[4] = {0, 0, 0, 0};
+    uint32_t shown_x = 0xffffffffu;
     if (lane < nvalid) {
-        if (done && p.auto_reset) {  // clear() (ref:306-315): the reset observation is the empty board
+        p.reward[(size_t)t * n_envs + e] = (float)reward;
+        p.done[(size_t)t * n_envs + e] = (unsigned char)done;
+        if (done && p.stats) {  // episode statistics (K4), from the counters as the terminal step left them
+            atomicAdd(p.stats, 1ull);
+            atomicAdd(p.stats + 1, (unsigned long long)(long long)(int)rec.w[2]);
+            atomicAdd(p.stats + 2, (unsigned long long)(long long)(int)rec.w[4]);
+            atomicAdd(p.stats + 3, (unsigned long long)(long long)(int)rec.w[3]);
+        }
+        if (resets) {
+            for (int i = 0; i < W * CW; ++i) rec.w[kStateWords + i] = 0u;
+        } else {
+            const Piece pc = unpack_piece((int)rec.w[0]);
+            if (pc.id < 7) {
+                const PieceCols<ColT> q = tpe_piece_cols<ColT>(s_cells + 28, pc.id, pc.rot, pc.x, pc.y, W, H);
+                ColT under[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) under[c] = q.X[c] >= 0 ? rec.col(q.X[c]) : 0;
+                shown_x = 0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (q.X[c] >= 0) rec.set_col(q.X[c], under[c] | q.m[c]);
+                    shown_m[c] = q.m[c];
+                    shown_x |= (uint32_t)(q.X[c] & 0xff) << (8 * c);
+                }
+            }
+        }
+    }
+    TPE_MARK(3);
+    // the staging block is free once the previous bulk store has READ it (its writes may still be in flight)
+    if (staged && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
+    TPE_MARK(4);
+
+    // 4. observations: float32 [W][H] per env (ref:421-424, 400).  One lane per (env, column): the column's cells are
+    //    consecutive in the observation, (env, column) pairs are consecutive in the group's block.
+    if (p.obs && !staged) {
+        // direct 16-byte stores, lane = float4 slot of the group's block (512 contiguous bytes per warp instruction);
+        // needs H % 4 == 0 (the launcher stages everything else)
+        const int hq = H >> 2, nq = W * hq, total = nvalid * nq;
+        unsigned char *dst = reinterpret_cast<unsigned char *>(p.obs) +
+                             ((long long)t * p.obs_t_stride + e0 * (long long)p.obs_elems) * (u8 ? 1 : 4);
+        constexpr int U = 4;  // slots in flight per lane: the column words, then the table entries, then the stores
+        for (int base = lane; base < total; base += 32 * U) {
+            uint32_t nib[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int idx = min(base + 32 * u, total - 1);  // clamped: the loads need no predicate, only the stores do
+                const int r = (WCT && HCT) ? idx / nq : (int)__umulhi((uint32_t)idx, p.inv_nq32);
+                const int q = idx - r * nq;
+                const int x = (WCT && HCT) ? q / hq : (int)(((uint32_t)q * p.inv_hq20) >> 20);
+                const int yq = q - x * hq;
+                nib[u] = (recs[r * pitch + kStateWords + CW * x + (yq >> 3)] >> (4 * (yq & 7))) & 15u;
+            }
+            if (!u8) {
+                float4 v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) v[u] = s_lut[nib[u]];
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (base + 32 * u < total) stg128(reinterpret_cast<float4 *>(dst) + base + 32 * u, v[u], pol_out);
+            } else {
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (base + 32 * u < total)
+                        stg32(reinterpret_cast<uint32_t *>(dst) + base + 32 * u, (nib[u] * 0x00204081u) & 0x01010101u, pol_out);
+            }
+        }
+        __syncwarp();
+    } else if (p.obs) {
+        const int items = nvalid * W;
+        if ((H & 3) == 0) {
+            const int hq = H >> 2;
+            for (int it = lane; it < items; it += 32) {
+                const int r = WCT ? it / W : (int)(((uint32_t)it * p.inv_w20) >> 20);
+                const int x = it - r * W;
+                const uint32_t *cw = recs + r * pitch + kStateWords + CW * x;
+                if (!u8) {
+                    float4 *dst = reinterpret_cast<float4 *>(stage) + it * hq;
+#pragma unroll
+                    for (int k = 0; k < hq; ++k) dst[k] = s_lut[(cw[k >> 3] >> (4 * (k & 7))) & 15u];
+                } else {
+                    uint32_t *dst = reinterpret_cast<uint32_t *>(stage) + it * hq;
+#pragma unroll
+                    for (int k = 0; k < hq; ++k)  // bit b of the nibble -> byte b (the four partial products do not overlap)
+                        dst[k] = (((cw[k >> 3] >> (4 * (k & 7))) & 15u) * 0x00204081u) & 0x01010101u;
+                }
+            }
+        } else {
+            for (int it = lane; it < items; it += 32) {
+                const int r = WCT ? it / W : (int)(((uint32_t)it * p.inv_w20) >> 20);
+                const int x = it - r * W;
+                const uint32_t *cw = recs + r * pitch + kStateWords + CW * x;
+                for (int y = 0; y < H; ++y) {
+                    const bool on = ((cw[y >> 5] >> (y & 31)) & 1u) != 0u;
+                    if (u8) stage[it * H + y] = on ? 1 : 0;
+                    else reinterpret_cast<float *>(stage)[it * H + y] = on ? 1.0f : 0.0f;
+                }
+            }
+        }
+        unsigned char *dst = reinterpret_cast<unsigned char *>(p.obs) +
+                             ((long long)t * p.obs_t_stride + e0 * (long long)p.obs_elems) * (u8 ? 1 : 4);
+        const uint32_t bytes = (uint32_t)(nvalid * nel * (u8 ? 1 : 4));
+        if (((reinterpret_cast<uintptr_t>(dst) | bytes) & 15) == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // every lane: its staging writes, for the TMA engine
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(stage)), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else {  // ragged tail of a uint8 batch / odd boards: plain stores from the staging block
+            __syncwarp();
+            if (((reinterpret_cast<uintptr_t>(dst) | bytes) & 3) == 0)
+                for (uint32_t i = lane; i < (bytes >> 2); i += 32) reinterpret_cast<uint32_t *>(dst)[i] = reinterpret_cast<const uint32_t *>(stage)[i];
+            else
+                for (uint32_t i = lane; i < bytes; i += 32) dst[i] = stage[i];
+            __syncwarp();
+        }
+    } else {
+        __syncwarp();
+    }
+
+    TPE_MARK(5);
+    // 5. info: the counters as the step left them, before any reset (reward and done went out before the observation)
+    if (p.info) {
+        int32_t *g_info = p.info + (long long)t * p.info_t_stride + e0 * kStateWords;
+        const int ninfo = nvalid * kStateWords;
+        for (int base = lane; base < ninfo; base += 128) {
+            uint32_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = min(base + 32 * u, ninfo - 1);
+                const int r = (j * 4370) >> 16;  // j / 15 for j < 480
+                const int c = j - r * kStateWords;
+                v[u] = recs[r * pitch + c];
+                v[u] = c == 0 ? (v[u] & 15u) : v[u];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (base + 32 * u < ninfo) stg32(g_info + base + 32 * u, v[u], pol_out);
+        }
+    }
+    __syncwarp();
+    // 6. _set_piece(False) (ref:303), literally: the cells of the piece are cleared on the board; an auto-reset env
+    //    gets the rest of clear(): zeroed episode counters and a fresh piece
+    if (lane < nvalid) {
+        ColT shown_c[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int X = (int)((shown_x >> (8 * c)) & 0xffu);
+            shown_c[c] = X != 0xff ? rec.col(X) : 0;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int X = (int)((shown_x >> (8 * c)) & 0xffu);
+            if (X != 0xff) rec.set_col(X, shown_c[c] & ~shown_m[c]);
+        }
+        if (resets) {
 #pragma unroll
             for (int i = 2; i <= 6; ++i) rec.w[i] = 0u;
             Piece pc;
             pc.id = tpe_spawn(rec, p, e, errbits);
             pc.rot = 0; pc.x = W / 2; pc.y = 0;
             rec.w[0] = (uint32_t)pack_piece(pc);
-            for (int i = 0; i < W * CW; ++i) rec.w[kStateWords + i] = 0u;
-        } else {
-            const Piece pc = unpack_piece((int)rec.w[0]);
-            if (pc.id < 7) {  // _set_piece(True) (ref:301)
-                const Cells cl = tpe_cells(s_cells, pc.id, pc.rot);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int X = pc.x + cl.i[k], Y = pc.y + cl.j[k];
-                    if (Y >= 0 && Y < H && (unsigned)X < (unsigned)W) {
-                        pX[k] = X; pY[k] = Y;
-                        rec.set_col(X, rec.col(X) | ((ColT)1 << Y));
-                    }
-                }
-            }
         }
-    }
-    __syncwarp();
-
-    // 4. observations: float32 [W][H] per env (ref:421-424, 400); 16-byte stores when H % 4 == 0, else 4-byte ones
-    if (p.obs && (H & 3) != 0) {
-        char *o = reinterpret_cast<char *>(p.obs) + ((long long)t * p.obs_t_stride + e0 * (long long)p.obs_elems) * (u8 ? 1 : 4);
-        for (int i0 = 0; i0 < nel; i0 += 32) {
-            const int i = i0 + lane;
-            const int x = (int)(((uint32_t)i * p.inv_h20) >> 20);
-            const int yy = i - x * H;
-            if (i < nel) {
-                const int wi = kStateWords + CW * x + (yy >> 5), sh = yy & 31;
-                for (int r = 0; r < nvalid; ++r) {
-                    const bool on = ((recs[r * pitch + wi] >> sh) & 1u) != 0u;
-                    if (u8) reinterpret_cast<unsigned char *>(o)[r * nel + i] = on ? 1 : 0;
-                    else reinterpret_cast<float *>(o)[r * nel + i] = on ? 1.0f : 0.0f;
-                }
-            }
-        }
-    } else if (p.obs) {
-        const int hq = H >> 2, nq = W * hq;
-        char *o4 = reinterpret_cast<char *>(p.obs) + ((long long)t * p.obs_t_stride + e0 * (long long)p.obs_elems) * (u8 ? 1 : 4);
-        for (int q0 = 0; q0 < nq; q0 += 32) {
-            const int q = q0 + lane;
-            const int x = (int)(((uint32_t)q * p.inv_hq20) >> 20);
-            const int yq = q - x * hq;
-            if (q < nq) {  // cells (x, 4 yq .. 4 yq + 3) are four adjacent bits of column x
-                const int wi = kStateWords + CW * x + (yq >> 3), sh = 4 * (yq & 7);
-                for (int r = 0; r < nvalid; ++r) {
-                    const uint32_t b = recs[r * pitch + wi] >> sh;
-                    const float4 v = make_float4((b & 1u) ? 1.0f : 0.0f, (b & 2u) ? 1.0f : 0.0f, (b & 4u) ? 1.0f : 0.0f,
-                                                 (b & 8u) ? 1.0f : 0.0f);
-                    store4(o4, (size_t)(r * nq + q), v, u8);
-                }
-            }
-        }
-    }
-    __syncwarp();
-
-    // 5. _set_piece(False) (ref:303), literally: the cells of the piece are cleared on the board
-    if (lane < nvalid) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (pX[k] >= 0) rec.set_col(pX[k], rec.col(pX[k]) & ~((ColT)1 << pY[k]));
     }
     __syncwarp();
     }  // for t
-    if (vec_ok) {
-        const int nvec = nwords >> 2;
-        for (int i = lane; i < nvec; i += 32) reinterpret_cast<uint4 *>(g_rec)[i] = reinterpret_cast<const uint4 *>(recs)[i];
-        for (int i = (nvec << 2) + lane; i < nwords; i += 32) g_rec[i] = recs[i];
-    } else {
-        for (int i = lane; i < nwords; i += 32) {
-            const int r = (int)(((uint32_t)i * p.inv_sw20) >> 20);
-            g_rec[i] = recs[r * pitch + (i - r * SW)];
+    {   // records back to HBM
+        uint32_t *g_rec = reinterpret_cast<uint32_t *>(p.state + e0 * (long long)p.stride);
+        const int nwords = nvalid * SW;
+        if (pitch == SW && (reinterpret_cast<uintptr_t>(g_rec) & 15) == 0) {
+            const int nvec = nwords >> 2;
+            for (int base = lane; base < nvec; base += 128) {
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = reinterpret_cast<const uint4 *>(recs)[min(base + 32 * u, nvec - 1)];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (base + 32 * u < nvec) stg128(reinterpret_cast<uint4 *>(g_rec) + base + 32 * u, v[u], pol_state);
+            }
+            for (int i = (nvec << 2) + lane; i < nwords; i += 32) g_rec[i] = recs[i];
+        } else {
+            for (int i = lane; i < nwords; i += 32) {
+                const int r = (int)(((uint32_t)i * p.inv_sw20) >> 20);
+                g_rec[i] = recs[r * pitch + (i - r * SW)];
+            }
         }
     }
+    __syncwarp();
+    TPE_MARK(6);
+    }  // for g
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (staged && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the TMA reads
+#if ST_TPE_TRACE
+    if (g_tpe_trace && lane == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        g_tpe_trace[((size_t)(p.draw_piece & 7) * kTraceWarps + (size_t)blockIdx.x * wpc + warp) * 16 + 7] = tpe_now();
+        g_tpe_trace[((size_t)(p.draw_piece & 7) * kTraceWarps + (size_t)blockIdx.x * wpc + warp) * 16 + 8] = smid;
+    }
+#endif
     errbits = __reduce_or_sync(FULL, errbits);
     if (errbits && p.err && lane == 0) atomicOr(p.err, errbits);
 }
 
-template <typename ColT>
-static cudaError_t launch_tpe_t(const Params &p, cudaStream_t stream)
+// Launch shape of the thread-per-env kernel: envs per group, warps per CTA, grid cap (CTAs per SM; 0 = one group per warp).
+struct TpeShape {
+    int epw, wpc, ctas_per_sm, staged;
+};
+
+static size_t tpe_smem_bytes(const Params &p, int epw, int wpc, int staged)
 {
-    const long long nwarps = (p.n + p.tpe_epw - 1) / p.tpe_epw;
-    const long long nctas = (nwarps + kTpeWarps - 1) / kTpeWarps;
     const int pitch = (p.stride >> 2) | 1;
-    const size_t smem = (size_t)kTpeWarps * p.tpe_epw * pitch * 4;
+    const int rec_words = (epw * pitch + 3) & ~3;
+    const int stage_words = staged ? (epw * p.W * p.H * (p.obs_u8 ? 1 : 4) + 15) >> 4 << 2 : 0;
+    return (size_t)wpc * (2 * rec_words + stage_words) * 4;
+}
+
+constexpr size_t kTpeSmemMax = 227 * 1024 - 1024;  // per CTA, minus the static tables and the per-CTA reserve
+
+template <typename ColT, int WCT, int HCT>
+static cudaError_t launch_tpe_t(const Params &p, const TpeShape &s, cudaStream_t stream)
+{
+    const long long ngroups = (p.n + s.epw - 1) / s.epw;
+    long long nctas = (ngroups + s.wpc - 1) / s.wpc;
+    const size_t smem = tpe_smem_bytes(p, s.epw, s.wpc, s.staged);
     static const bool pdl = getenv("ST_B200_NO_PDL") == nullptr;
-    if (smem > 48 * 1024)
-        cudaFuncSetAttribute(st_step_tpe_kernel<ColT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static bool attr_set[64] = {};
+    static int n_sm[64] = {};
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(st_step_tpe_kernel<ColT, WCT, HCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTpeSmemMax);
+        if (e != cudaSuccess) return e;
+        cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev);
+        attr_set[dev] = true;
+    }
+    if (s.ctas_per_sm > 0 && dev >= 0 && dev < 64 && n_sm[dev] > 0) {
+        const long long cap = (long long)s.ctas_per_sm * n_sm[dev];
+        nctas = nctas < cap ? nctas : cap;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)nctas);
-    cfg.blockDim = dim3(32 * kTpeWarps);
+    cfg.blockDim = dim3(32 * s.wpc);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -492,7 +789,7 @@ static cudaError_t launch_tpe_t(const Params &p, cudaStream_t stream)
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     count_launch();
-    return cudaLaunchKernelEx(&cfg, st_step_tpe_kernel<ColT>, p);
+    return cudaLaunchKernelEx(&cfg, st_step_tpe_kernel<ColT, WCT, HCT>, p);
 }
 
 // Round-1 measurements of the row-bitboard version of this kernel (tools/ram_path_sweep.py, us per step; 10x20 /
@@ -502,23 +799,60 @@ static cudaError_t launch_tpe_t(const Params &p, cudaStream_t stream)
 //   65536    34.8    22.6    20.5     27.7      |   50.8    49.1    59.2     73.4
 //   1048576  487.5   253.6   186.4    246.5     |  733.1   652.9   703.2    738.4
 static long long tpe_min_envs(const Params &p) { return p.H <= 31 ? 24576 : 65536; }
-static int tpe_default_epw(const Params &p) { return (p.H <= 31 && p.n >= 49152) ? 16 : 8; }
 
-// Thread-per-env path: single-step ram launches.
+static int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+static TpeShape tpe_shape(const Params &p)
+{
+    TpeShape s;
+    s.epw = env_int("ST_B200_TPE_EPW", (p.H <= 31 && p.n >= 49152) ? 16 : 8);
+    if (s.epw != 4 && s.epw != 8 && s.epw != 16 && s.epw != 32) s.epw = 32;
+    s.wpc = env_int("ST_B200_TPE_WPC", 4);
+    if (s.wpc != 1 && s.wpc != 2 && s.wpc != 4 && s.wpc != 8) s.wpc = 4;
+    // boards whose columns are not whole float4s always go through the staging block
+    s.staged = (p.H & 3) != 0 ? 1 : env_int("ST_B200_TPE_STAGED", 0);
+    while (s.wpc > 1 && tpe_smem_bytes(p, s.epw, s.wpc, s.staged) > kTpeSmemMax) s.wpc >>= 1;
+    while (s.epw > 4 && tpe_smem_bytes(p, s.epw, s.wpc, s.staged) > kTpeSmemMax) s.epw >>= 1;
+    s.ctas_per_sm = env_int("ST_B200_TPE_CTAS_PER_SM", 0);
+    return s;
+}
+
+// Thread-per-env path: ram observations, single-step launches and st_step_many alike.
 static bool tpe_eligible(const Params &p, int obs_type)
 {
-    return obs_type == 0 && p.mode == MODE_STEP && p.n > 0 && (p.obs_t_stride & 3) == 0;
+    return obs_type == 0 && p.mode == MODE_STEP && p.n > 0 && (p.obs_t_stride & 3) == 0 &&
+           tpe_smem_bytes(p, 4, 1, 1) <= kTpeSmemMax;
 }
 
 static cudaError_t launch_tpe(const Params &p0, cudaStream_t stream)
 {
     Params p = p0;
-    // envs per warp: the per-warp engine chain is the same for 8 or 32 envs, so mid-size batches get more warps
-    const char *ov = getenv("ST_B200_TPE_EPW");
-    p.tpe_epw = ov ? atoi(ov) : tpe_default_epw(p);
-    if (p.tpe_epw != 4 && p.tpe_epw != 8 && p.tpe_epw != 16 && p.tpe_epw != 32) p.tpe_epw = 32;
-    if (p.col_words == 1) return launch_tpe_t<uint32_t>(p, stream);
-    return launch_tpe_t<unsigned long long>(p, stream);
+    const TpeShape s = tpe_shape(p);
+    p.tpe_epw = s.epw;
+    p.tpe_staged = s.staged;
+    p.tpe_l2 = env_int("ST_B200_TPE_L2", 0);
+#if ST_TPE_TRACE
+    static int launch_id = 0;
+    p.draw_piece = launch_id++;  // unused by step launches: which of the 8 trace slabs this launch writes
+#endif
+    if (p.col_words == 1) {
+        if (p.W == 10 && p.H == 20) return launch_tpe_t<uint32_t, 10, 20>(p, s, stream);
+        return launch_tpe_t<uint32_t, 0, 0>(p, s, stream);
+    }
+    if (p.W == 20 && p.H == 40) return launch_tpe_t<unsigned long long, 20, 40>(p, s, stream);
+    return launch_tpe_t<unsigned long long, 0, 0>(p, s, stream);
 }
 
 }  // namespace st
+
+#if ST_TPE_TRACE
+// profiling builds only (never part of the product library): where the kernel writes its phase timestamps
+extern "C" __attribute__((visibility("default"))) int st_debug_set_tpe_trace(unsigned long long *buf)
+{
+    return (int)cudaMemcpyToSymbol(st::g_tpe_trace, &buf, sizeof(buf));
+}
+#endif

@@ -48,7 +48,7 @@ __device__ __forceinline__ unsigned long long tpe_now()
 }
 #define TPE_MARK(slot)                                                                                        \
     do {                                                                                                      \
-        if (g_tpe_trace && lane == 0 && g == (long long)blockIdx.x * wpc + warp)                              \
+        if (g_tpe_trace && lane == 0 && g == (long long)blockIdx.x * wpc + warp && (size_t)g < kTraceWarps)     \
             g_tpe_trace[((size_t)(p.draw_piece & 7) * kTraceWarps + (size_t)blockIdx.x * wpc + warp) * 16 + (slot)] = tpe_now(); \
     } while (0)
 #else
@@ -399,6 +399,17 @@ __device__ __forceinline__ unsigned long long l2_policy(int kind)  // 0 normal, 
     else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
+#ifndef ST_TPE_PLAIN_ST
+#define ST_TPE_PLAIN_ST 0  // experiment knob: 1 = ordinary stores without L2 cache hints
+#endif
+#ifndef ST_TPE_NO_CPASYNC
+#define ST_TPE_NO_CPASYNC 0  // experiment knob: 1 = records through registers (LDG + STS) instead of cp.async
+#endif
+#if ST_TPE_PLAIN_ST
+__device__ __forceinline__ void stg128(void *ptr, const float4 &v, unsigned long long) { *reinterpret_cast<float4 *>(ptr) = v; }
+__device__ __forceinline__ void stg128(void *ptr, const uint4 &v, unsigned long long) { *reinterpret_cast<uint4 *>(ptr) = v; }
+__device__ __forceinline__ void stg32(void *ptr, uint32_t v, unsigned long long) { *reinterpret_cast<uint32_t *>(ptr) = v; }
+#else
 __device__ __forceinline__ void stg128(void *ptr, const float4 &v, unsigned long long pol)
 {
     asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol));
@@ -411,6 +422,7 @@ __device__ __forceinline__ void stg32(void *ptr, uint32_t v, unsigned long long 
 {
     asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(ptr), "r"(v), "l"(pol));
 }
+#endif
 
 // Records of one group: HBM -> shared memory, asynchronously (one cp.async group per call, possibly empty).
 __device__ __forceinline__ void tpe_fetch(uint32_t *recs, const unsigned char *state, long long e0, int nvalid, int SW, int pitch,
@@ -419,6 +431,13 @@ __device__ __forceinline__ void tpe_fetch(uint32_t *recs, const unsigned char *s
     if (nvalid > 0) {
         const uint32_t *g_rec = reinterpret_cast<const uint32_t *>(state + e0 * (long long)stride);
         const int nwords = nvalid * SW;
+#if ST_TPE_NO_CPASYNC
+        if (pitch == SW && (reinterpret_cast<uintptr_t>(g_rec) & 15) == 0) {
+            const int nvec = nwords >> 2;
+            for (int i = lane; i < nvec; i += 32) reinterpret_cast<uint4 *>(recs)[i] = reinterpret_cast<const uint4 *>(g_rec)[i];
+            for (int i = (nvec << 2) + lane; i < nwords; i += 32) recs[i] = g_rec[i];
+        } else
+#endif
         if (pitch == SW && (reinterpret_cast<uintptr_t>(g_rec) & 15) == 0) {  // contiguous in both, 16-byte aligned
             const int nvec = nwords >> 2;
             for (int i = lane; i < nvec; i += 32)
@@ -447,7 +466,7 @@ __global__ void __launch_bounds__(32 * kTpeMaxWarps, ST_TPE_MINBLOCKS) st_step_t
     asm volatile("griddepcontrol.launch_dependents;");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
 #if ST_TPE_TRACE
-    if (g_tpe_trace && lane == 0)
+    if (g_tpe_trace && lane == 0 && (size_t)blockIdx.x * wpc + warp < kTraceWarps)
         g_tpe_trace[((size_t)(p.draw_piece & 7) * kTraceWarps + (size_t)blockIdx.x * wpc + warp) * 16 + 9] = tpe_now();
 #endif
     for (int i = threadIdx.x; i < 56; i += blockDim.x) s_cells[i] = i < 28 ? c_cells.e[i] : c_cells.c[i - 28];
@@ -463,7 +482,8 @@ __global__ void __launch_bounds__(32 * kTpeMaxWarps, ST_TPE_MINBLOCKS) st_step_t
     // warp-private shared memory: two record buffers (this group, next group), then the observation staging block
     const int rec_words = (epw * pitch + 3) & ~3;
     const bool staged = p.tpe_staged != 0;
-    const int stage_words = staged ? (epw * nel * (u8 ? 1 : 4) + 15) >> 4 << 2 : 0;
+    // staged: the group's observation block; direct: one byte per float4 slot of that block (the table offset)
+    const int stage_words = staged ? (epw * nel * (u8 ? 1 : 4) + 15) >> 4 << 2 : (epw * (nel >> 2) + 15) >> 4 << 2;
     uint32_t *const wbase = s_dyn + (size_t)warp * (2 * rec_words + stage_words);
     unsigned char *const stage = reinterpret_cast<unsigned char *>(wbase + 2 * rec_words);
     const long long ngroups = (p.n + epw - 1) / epw;
@@ -573,27 +593,40 @@ __global__ void __launch_bounds__(32 * kTpeMaxWarps, ST_TPE_MINBLOCKS) st_step_t
     // 4. observations: float32 [W][H] per env (ref:421-424, 400).  One lane per (env, column): the column's cells are
     //    consecutive in the observation, (env, column) pairs are consecutive in the group's block.
     if (p.obs && !staged) {
-        // direct 16-byte stores, lane = float4 slot of the group's block (512 contiguous bytes per warp instruction);
-        // needs H % 4 == 0 (the launcher stages everything else)
-        const int hq = H >> 2, nq = W * hq, total = nvalid * nq;
+        // direct 16-byte stores; needs H % 4 == 0 (the launcher stages everything else).  Two passes, each with the
+        // lane mapping that makes its addressing trivial:
+        //  a. one lane per (env, column): the column's H / 4 nibbles go into a byte array in slot order — (env, column)
+        //     pairs and the float4 slots of a column are both consecutive in the group's block — as table OFFSETS;
+        //  b. one lane per float4 slot: byte -> table entry -> store, 512 contiguous bytes per warp instruction, with
+        //     U independent stores in flight per lane (a store holds its source registers until the LSU has read them)
+        const int hq = H >> 2, nq = W * hq, total = nvalid * nq, items = nvalid * W;
+        for (int it = lane; it < items; it += 32) {
+            const int r = WCT ? (int)((unsigned)it / (unsigned)W) : (int)(((uint32_t)it * p.inv_w20) >> 20);
+            const int x = it - r * W;
+            const uint32_t *cw = recs + r * pitch + kStateWords + CW * x;
+            unsigned char *d = stage + it * hq;
+            if constexpr (CW == 1) {
+                const uint32_t w = cw[0] << 4;
+#pragma unroll
+                for (int k = 0; k < hq; ++k) d[k] = (unsigned char)((w >> (4 * k)) & 0xf0u);
+            } else {
+                const unsigned long long w = ((unsigned long long)cw[1] << 32) | cw[0];
+#pragma unroll
+                for (int k = 0; k < hq; ++k) d[k] = (unsigned char)(((w >> (4 * k)) & 15u) << 4);
+            }
+        }
+        __syncwarp();
         unsigned char *dst = reinterpret_cast<unsigned char *>(p.obs) +
                              ((long long)t * p.obs_t_stride + e0 * (long long)p.obs_elems) * (u8 ? 1 : 4);
-        constexpr int U = 4;  // slots in flight per lane: the column words, then the table entries, then the stores
+        constexpr int U = 4;
         for (int base = lane; base < total; base += 32 * U) {
-            uint32_t nib[U];
+            uint32_t off[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int idx = min(base + 32 * u, total - 1);  // clamped: the loads need no predicate, only the stores do
-                const int r = (WCT && HCT) ? idx / nq : (int)__umulhi((uint32_t)idx, p.inv_nq32);
-                const int q = idx - r * nq;
-                const int x = (WCT && HCT) ? q / hq : (int)(((uint32_t)q * p.inv_hq20) >> 20);
-                const int yq = q - x * hq;
-                nib[u] = (recs[r * pitch + kStateWords + CW * x + (yq >> 3)] >> (4 * (yq & 7))) & 15u;
-            }
+            for (int u = 0; u < U; ++u) off[u] = stage[min(base + 32 * u, total - 1)];  // clamped: only the stores are predicated
             if (!u8) {
                 float4 v[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) v[u] = s_lut[nib[u]];
+                for (int u = 0; u < U; ++u) v[u] = *reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(s_lut) + off[u]);
 #pragma unroll
                 for (int u = 0; u < U; ++u)
                     if (base + 32 * u < total) stg128(reinterpret_cast<float4 *>(dst) + base + 32 * u, v[u], pol_out);
@@ -601,7 +634,7 @@ __global__ void __launch_bounds__(32 * kTpeMaxWarps, ST_TPE_MINBLOCKS) st_step_t
 #pragma unroll
                 for (int u = 0; u < U; ++u)
                     if (base + 32 * u < total)
-                        stg32(reinterpret_cast<uint32_t *>(dst) + base + 32 * u, (nib[u] * 0x00204081u) & 0x01010101u, pol_out);
+                        stg32(reinterpret_cast<uint32_t *>(dst) + base + 32 * u, ((off[u] >> 4) * 0x00204081u) & 0x01010101u, pol_out);
             }
         }
         __syncwarp();
@@ -731,7 +764,7 @@ __global__ void __launch_bounds__(32 * kTpeMaxWarps, ST_TPE_MINBLOCKS) st_step_t
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (staged && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the TMA reads
 #if ST_TPE_TRACE
-    if (g_tpe_trace && lane == 0) {
+    if (g_tpe_trace && lane == 0 && (size_t)blockIdx.x * wpc + warp < kTraceWarps) {
         unsigned smid;
         asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
         g_tpe_trace[((size_t)(p.draw_piece & 7) * kTraceWarps + (size_t)blockIdx.x * wpc + warp) * 16 + 7] = tpe_now();
@@ -751,7 +784,7 @@ static size_t tpe_smem_bytes(const Params &p, int epw, int wpc, int staged)
 {
     const int pitch = (p.stride >> 2) | 1;
     const int rec_words = (epw * pitch + 3) & ~3;
-    const int stage_words = staged ? (epw * p.W * p.H * (p.obs_u8 ? 1 : 4) + 15) >> 4 << 2 : 0;
+    const int stage_words = staged ? (epw * p.W * p.H * (p.obs_u8 ? 1 : 4) + 15) >> 4 << 2 : (epw * (p.W * p.H >> 2) + 15) >> 4 << 2;
     return (size_t)wpc * (2 * rec_words + stage_words) * 4;
 }
 
@@ -792,13 +825,25 @@ static cudaError_t launch_tpe_t(const Params &p, const TpeShape &s, cudaStream_t
     return cudaLaunchKernelEx(&cfg, st_step_tpe_kernel<ColT, WCT, HCT>, p);
 }
 
-// Round-1 measurements of the row-bitboard version of this kernel (tools/ram_path_sweep.py, us per step; 10x20 /
-// 20 wide x 40 high boards) — kept as the baseline the column version is compared with in DESIGN.md:
-//   n        warp    8/warp  16/warp  32/warp   |   warp    8/warp  16/warp  32/warp
-//   8192     8.2     12.5    11.9     11.2      |   10.7    22.3    20.9     21.3
-//   65536    34.8    22.6    20.5     27.7      |   50.8    49.1    59.2     73.4
-//   1048576  487.5   253.6   186.4    246.5     |  733.1   652.9   703.2    738.4
-static long long tpe_min_envs(const Params &p) { return p.H <= 31 ? 24576 : 65536; }
+// Which batches take this kernel and with how many envs per group: measured on B200 (tools/knob_sweep.py, profiles/
+// r2_ram_path_sweep_after.txt; us per single-step launch, 10x20 boards / 20 wide x 40 high boards):
+//   n        warp-per-env   epw 4    epw 8    epw 16   epw 32  |  warp-per-env   epw 4    epw 8    epw 16
+//   8192         7.8         8.0      9.1      9.5      8.1    |     12.0         12.3     16.8     14.7
+//   16384       13.1         8.6      9.2     11.8      9.5    |     20.2         14.3     18.4     25.3
+//   32768       23.3        14.4     10.2     13.4     17.3    |     36.8         25.0     23.2     31.8
+//   65536       43.1        25.5     16.4     15.0     18.8    |     69.4         42.2     38.6     41.7
+//   262144     162.6        92.8     56.9     45.4     49.2    |    265.6        171.6    155.9    155.3
+// The per-warp engine chain costs the same for 4 or 32 envs, so mid-size batches get fewer envs per warp (more warps
+// to hide its latency) and large ones more (fewer instructions per env).
+// T steps per launch (records stay in shared memory between steps): 8 envs per group from 6144 envs up
+// (10x20, us per step at T = 32: 8192 envs 2.9 against 3.8 warp-per-env, 32768 envs 6.1 / 13.4, 65536 envs 9.8 / 24.6).
+static long long tpe_min_envs(const Params &p) { return p.T > 1 ? 6144 : 10240; }
+static int tpe_default_epw(const Params &p)
+{
+    if (p.T > 1) return 8;
+    if (p.H <= 31) return p.n < 20480 ? 4 : p.n < 57344 ? 8 : 16;
+    return p.n < 24576 ? 4 : 8;
+}
 
 static int env_int(const char *name, int dflt)
 {
@@ -809,7 +854,7 @@ static int env_int(const char *name, int dflt)
 static TpeShape tpe_shape(const Params &p)
 {
     TpeShape s;
-    s.epw = env_int("ST_B200_TPE_EPW", (p.H <= 31 && p.n >= 49152) ? 16 : 8);
+    s.epw = env_int("ST_B200_TPE_EPW", tpe_default_epw(p));
     if (s.epw != 4 && s.epw != 8 && s.epw != 16 && s.epw != 32) s.epw = 32;
     s.wpc = env_int("ST_B200_TPE_WPC", 4);
     if (s.wpc != 1 && s.wpc != 2 && s.wpc != 4 && s.wpc != 8) s.wpc = 4;
@@ -834,7 +879,7 @@ static cudaError_t launch_tpe(const Params &p0, cudaStream_t stream)
     const TpeShape s = tpe_shape(p);
     p.tpe_epw = s.epw;
     p.tpe_staged = s.staged;
-    p.tpe_l2 = env_int("ST_B200_TPE_L2", 0);
+    p.tpe_l2 = env_int("ST_B200_TPE_L2", 1);  // observations / info leave as evict_first streams (measured: -3..5 %)
 #if ST_TPE_TRACE
     static int launch_id = 0;
     p.draw_piece = launch_id++;  // unused by step launches: which of the 8 trace slabs this launch writes

@@ -68,17 +68,17 @@ class VecEnv:
         self.single_observation_shape = obs_shape(width, height, obs_type if obs_type in native.OBS_TYPES else "rgb",
                                                   extend_dims)
         n, dev = self.num_envs, self.device
-        self.state = torch.zeros(n * self.state_stride, dtype=torch.uint8, device=dev)
-        self.obs = torch.zeros((n,) + self.single_observation_shape, dtype=obs_dtype, device=dev)
-        self.reward = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.done = torch.zeros(n, dtype=torch.bool, device=dev)
-        self.info_buf = torch.zeros((n, ST_INFO_WORDS), dtype=torch.int32, device=dev) if with_info else None
-        self.err = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.stats = torch.zeros(ST_STATS_WORDS, dtype=torch.int64, device=dev)
+        self.state = self._zeros(n * self.state_stride, torch.uint8)
+        self.obs = self._zeros((n,) + self.single_observation_shape, obs_dtype)
+        self.reward = self._zeros(n, torch.float32)
+        self.done = self._zeros(n, torch.bool)
+        self.info_buf = self._zeros((n, ST_INFO_WORDS), torch.int32) if with_info else None
+        self.err = self._zeros(1, torch.int32)
+        self.stats = self._zeros(ST_STATS_WORDS, torch.int64)
         self._queue = None
         # gym<=0.25 vector envs report the last observation of a finished episode in info["terminal_observation"]
         # (the returned obs is already the reset one); optional because it is a second observation-sized buffer
-        self.term_obs = torch.zeros_like(self.obs) if (terminal_obs and auto_reset) else None
+        self.term_obs = self._zeros(tuple(self.obs.shape), obs_dtype) if (terminal_obs and auto_reset) else None
         self._aux = StAux(None, 0, 0, self.err.data_ptr(), self.stats.data_ptr(),
                           self.term_obs.data_ptr() if self.term_obs is not None else None)
         # per-step host cost matters for small batches: everything constant across steps is bound once
@@ -91,6 +91,15 @@ class VecEnv:
         self._check(self._L.st_init(C.byref(self.cfg), self.state.data_ptr(), n, self._stream()), "st_init")
 
     # ---- plumbing ----
+    def _zeros(self, shape, dtype):
+        """Every persistent device buffer the kernels write is allocated here, zero-filled (tests override `_empty` to
+        put guard bands around all of them)."""
+        return self._empty(shape, dtype).zero_()
+
+    def _empty(self, shape, dtype):
+        """Per-call outputs (rollout buffers, observe / render results): the kernels write every byte of them."""
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -157,12 +166,12 @@ class VecEnv:
         T = int(actions.shape[0])
         a = self._actions(actions, (T, self.num_envs))
         n, dev = self.num_envs, self.device
-        reward = torch.empty((T, n), dtype=torch.float32, device=dev)
-        done = torch.empty((T, n), dtype=torch.bool, device=dev)
-        obs = torch.empty((T,) + tuple(self.obs.shape), dtype=self.obs_dtype, device=dev) if rollout_obs else self.obs
+        reward = self._empty((T, n), torch.float32)
+        done = self._empty((T, n), torch.bool)
+        obs = self._empty((T,) + tuple(self.obs.shape), self.obs_dtype) if rollout_obs else self.obs
         info = self.info_buf
         if rollout_info and info is not None:
-            info = torch.empty((T, n, ST_INFO_WORDS), dtype=torch.int32, device=dev)
+            info = self._empty((T, n, ST_INFO_WORDS), torch.int32)
         self._check(self._L.st_step_many(
             C.byref(self.cfg), self.state.data_ptr(), a.data_ptr(), T, obs.data_ptr(),
             n * self.obs_elems if rollout_obs else 0, reward.data_ptr(), done.data_ptr(),
@@ -185,7 +194,7 @@ class VecEnv:
     def observe(self, draw_piece=True):
         """_observation(engine.render()) (tetris_env.py:317-321, 413-433) of the current state, no step."""
         self._live()
-        out = torch.empty_like(self.obs)
+        out = self._empty(tuple(self.obs.shape), self.obs_dtype)
         self._check(self._L.st_observe(C.byref(self.cfg), self.state.data_ptr(), int(bool(draw_piece)),
                                        out.data_ptr(), self.num_envs, self._stream()), "st_observe")
         return out
@@ -193,7 +202,7 @@ class VecEnv:
     def render(self, size=160, draw_piece=True):
         """Batched TetrisEnv.render('rgb_array') (tetris_env.py:458-462): uint8 [N, size, size, 3]."""
         self._live()
-        out = torch.empty((self.num_envs, size, size, 3), dtype=torch.uint8, device=self.device)
+        out = self._empty((self.num_envs, size, size, 3), torch.uint8)
         self._check(self._L.st_render(C.byref(self.cfg), self.state.data_ptr(), int(bool(draw_piece)), int(size),
                                       out.data_ptr(), self.num_envs, self._stream()), "st_render")
         return out

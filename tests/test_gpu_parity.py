@@ -901,3 +901,51 @@ def test_host_pipeline_matches_sync_and_oracle(st, kw, n, zc):
     pipe.reset()  # drains and discards
     assert pipe.poll_errors() == 0 and sync.poll_errors() == 0
     pipe.close(), sync.close()
+
+
+@pytest.mark.parametrize("kw,n", [
+    (dict(), 37), (dict(), 1029), (dict(width=20, height=40), 45), (dict(width=5, height=7, lock_delay=2), 67),
+    (dict(width=7, height=9, penalise_holes=True), 130), (dict(obs_type="grayscale", extend_dims=True), 13),
+    (dict(obs_type="rgb"), 11), (dict(obs_type="rgb", width=7, height=9), 19),
+    (dict(obs_dtype=torch.uint8), 37), (dict(width=6, height=12, obs_dtype=torch.uint8), 35),
+    (dict(obs_type="rgb", obs_dtype=torch.uint8), 11),
+])
+def test_no_write_outside_the_buffers(st, kw, n):
+    """compute-sanitizer is closed on the GPU pool (profiles/r2_compute_sanitizer_attempt.log), so out-of-bounds
+    writes are hunted with guard bands: every buffer a kernel writes (state, obs, terminal obs, reward, done, info,
+    error word, statistics, rollout buffers, observe / render outputs) sits inside a larger allocation filled with a
+    canary pattern, ragged batch sizes put the last warp / CTA / 16-byte store right at the end of each buffer, and
+    after step, step_many, masked reset, observe and render on both ram kernels every guard byte must be intact
+    (an out-of-bounds READ of this size would show up as a parity failure in the tests above: the guards hold 0xA5)."""
+    GUARD = 4096  # bytes on either side; a multiple of every alignment the kernels assume
+    arenas = []
+
+    class Guarded(st.VecEnv):
+        def _empty(self, shape, dtype):
+            numel = int(np.prod(shape)) if not isinstance(shape, int) else int(shape)
+            nbytes = numel * torch.empty((), dtype=dtype).element_size()
+            pad = (-nbytes) % 256
+            arena = torch.full((GUARD + nbytes + pad + GUARD,), 0xA5, dtype=torch.uint8, device=self.device)
+            arenas.append((arena, nbytes))
+            return arena[GUARD:GUARD + nbytes].view(dtype).view(shape)
+
+    env = Guarded(n, device="cuda:0", seed=5, terminal_obs=True, **kw)
+    env.reset()
+    acts = torch.from_numpy(np.random.RandomState(3).randint(0, 7, (40, n)).astype(np.uint8)).cuda()
+    for t in range(12):
+        env.step(acts[t])
+    env.step_many(acts[12:28], rollout_obs=True, rollout_info=True)
+    env.step_many(acts[28:40])
+    mask = torch.zeros(n, dtype=torch.bool, device="cuda")
+    mask[::3] = True
+    env.reset(mask=mask)
+    env.step(acts[0])
+    env.observe()
+    env.render()
+    assert env.poll_errors() == 0
+    torch.cuda.synchronize()
+    assert len(arenas) >= 12
+    for arena, nbytes in arenas:
+        a = arena.cpu().numpy()
+        assert (a[:GUARD] == 0xA5).all(), "write before a buffer"
+        assert (a[GUARD + nbytes:] == 0xA5).all(), "write past the end of a buffer"

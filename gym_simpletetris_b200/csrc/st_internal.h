@@ -56,6 +56,7 @@ struct Params {
     int draw_piece;
     int tpe_epw;     // thread-per-env kernel: envs per group (one group = one warp pass)
     int tpe_l2;      // thread-per-env kernel: L2 eviction hints (bit 0: outputs evict_first, bit 1: records evict_last)
+    int tpe_nrec;    // thread-per-env kernel: record buffers per warp (2 = next group prefetched; capped grids)
     int tpe_staged;  // thread-per-env kernel: observations through a shared-memory block + TMA bulk store
 };
 

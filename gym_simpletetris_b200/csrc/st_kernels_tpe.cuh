@@ -482,10 +482,12 @@ __global__ void __launch_bounds__(32 * kTpeMaxWarps, ST_TPE_MINBLOCKS) st_step_t
     // warp-private shared memory: two record buffers (this group, next group), then the observation staging block
     const int rec_words = (epw * pitch + 3) & ~3;
     const bool staged = p.tpe_staged != 0;
-    // staged: the group's observation block; direct: one byte per float4 slot of that block (the table offset)
-    const int stage_words = staged ? (epw * nel * (u8 ? 1 : 4) + 15) >> 4 << 2 : (epw * (nel >> 2) + 15) >> 4 << 2;
-    uint32_t *const wbase = s_dyn + (size_t)warp * (2 * rec_words + stage_words);
-    unsigned char *const stage = reinterpret_cast<unsigned char *>(wbase + 2 * rec_words);
+    // staged: two chunk buffers of 32 (env, column) items; direct: one byte per float4 slot of the group's block
+    const int chunk_bytes = (32 * H * (u8 ? 1 : 4) + 15) & ~15;
+    const int stage_words = staged ? 2 * chunk_bytes >> 2 : (epw * (nel >> 2) + 15) >> 4 << 2;
+    const int nrec = p.tpe_nrec;  // record buffers per warp: 2 when warps walk over several groups (next group in flight)
+    uint32_t *const wbase = s_dyn + (size_t)warp * (nrec * rec_words + stage_words);
+    unsigned char *const stage = reinterpret_cast<unsigned char *>(wbase + nrec * rec_words);
     const long long ngroups = (p.n + epw - 1) / epw;
     const long long gstride = (long long)gridDim.x * wpc;
     long long g = (long long)blockIdx.x * wpc + warp;
@@ -497,25 +499,28 @@ __global__ void __launch_bounds__(32 * kTpeMaxWarps, ST_TPE_MINBLOCKS) st_step_t
     int errbits = 0;
     const size_t n_envs = (size_t)p.n;
     const unsigned long long pol_out = l2_policy((p.tpe_l2 & 1) ? 1 : 0), pol_state = l2_policy((p.tpe_l2 & 2) ? 2 : 0);
-    {
+    if (nrec == 2) {
         const long long e0 = g * epw;
         const int nv = (int)(p.n - e0 < epw ? p.n - e0 : epw);
         tpe_fetch(wbase, p.state, e0, nv, SW, pitch, p.stride, p.inv_sw20, lane, pol_state);
     }
-    int cur = 0;
-    for (; g < ngroups; g += gstride, cur ^= 1) {
+    int cur = 0, chunk = 0;
+    for (; g < ngroups; g += gstride, cur ^= nrec - 1) {
     uint32_t *const recs = wbase + cur * rec_words;
     const long long e0 = g * epw;
     const int nvalid = (int)(p.n - e0 < epw ? p.n - e0 : epw);
     const long long e = e0 + lane;
     unsigned int action_u = 6u;  // issued before the wait so that its miss overlaps the record copy
     if (lane < nvalid) asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(action_u) : "l"(p.actions + e));
-    {   // 1. next group's records on their way; this group's have arrived
+    if (nrec == 2) {  // 1. next group's records on their way; this group's have arrived
         const long long gn = g + gstride;
         const long long en = gn * epw;
         const int nvn = gn < ngroups ? (int)(p.n - en < epw ? p.n - en : epw) : 0;
         tpe_fetch(wbase + (cur ^ 1) * rec_words, p.state, en, nvn, SW, pitch, p.stride, p.inv_sw20, lane, pol_state);
         asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+        tpe_fetch(wbase, p.state, e0, nvalid, SW, pitch, p.stride, p.inv_sw20, lane, pol_state);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncwarp();
     TPE_MARK(1);
@@ -585,8 +590,6 @@ __global__ void __launch_bounds__(32 * kTpeMaxWarps, ST_TPE_MINBLOCKS) st_step_t
         }
     }
     TPE_MARK(3);
-    // the staging block is free once the previous bulk store has READ it (its writes may still be in flight)
-    if (staged && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncwarp();
     TPE_MARK(4);
 
@@ -639,53 +642,59 @@ __global__ void __launch_bounds__(32 * kTpeMaxWarps, ST_TPE_MINBLOCKS) st_step_t
         }
         __syncwarp();
     } else if (p.obs) {
+        // staged: 32 (env, column) items at a time — H consecutive cells each, and consecutive items are consecutive
+        // in the group's block — are expanded into one of two warp-private chunk buffers, and ONE cp.async.bulk (TMA)
+        // store per chunk sends it on its way: no store instruction queues in the LSU in front of the other warps'
+        // shared-memory loads, and a buffer is only waited for when it comes round again two chunks later.
         const int items = nvalid * W;
-        if ((H & 3) == 0) {
-            const int hq = H >> 2;
-            for (int it = lane; it < items; it += 32) {
-                const int r = WCT ? it / W : (int)(((uint32_t)it * p.inv_w20) >> 20);
+        const int item_bytes = H * (u8 ? 1 : 4);
+        unsigned char *dstb = reinterpret_cast<unsigned char *>(p.obs) +
+                              ((long long)t * p.obs_t_stride + e0 * (long long)p.obs_elems) * (u8 ? 1 : 4);
+        for (int it0 = 0; it0 < items; it0 += 32, chunk ^= 1) {
+            unsigned char *buf = stage + chunk * chunk_bytes;
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // the store of two chunks ago has read `buf`
+            __syncwarp();
+            const int it = it0 + lane;
+            if (it < items) {
+                const int r = WCT ? (int)((unsigned)it / (unsigned)W) : (int)(((uint32_t)it * p.inv_w20) >> 20);
                 const int x = it - r * W;
                 const uint32_t *cw = recs + r * pitch + kStateWords + CW * x;
-                if (!u8) {
-                    float4 *dst = reinterpret_cast<float4 *>(stage) + it * hq;
+                unsigned char *d = buf + lane * item_bytes;
+                if ((H & 3) == 0) {
+                    const int hq = H >> 2;
+                    if (!u8) {
 #pragma unroll
-                    for (int k = 0; k < hq; ++k) dst[k] = s_lut[(cw[k >> 3] >> (4 * (k & 7))) & 15u];
+                        for (int k = 0; k < hq; ++k)
+                            reinterpret_cast<float4 *>(d)[k] = s_lut[(cw[k >> 3] >> (4 * (k & 7))) & 15u];
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < hq; ++k)  // bit b of the nibble -> byte b (the four partial products do not overlap)
+                            reinterpret_cast<uint32_t *>(d)[k] = (((cw[k >> 3] >> (4 * (k & 7))) & 15u) * 0x00204081u) & 0x01010101u;
+                    }
                 } else {
-                    uint32_t *dst = reinterpret_cast<uint32_t *>(stage) + it * hq;
-#pragma unroll
-                    for (int k = 0; k < hq; ++k)  // bit b of the nibble -> byte b (the four partial products do not overlap)
-                        dst[k] = (((cw[k >> 3] >> (4 * (k & 7))) & 15u) * 0x00204081u) & 0x01010101u;
+                    for (int y = 0; y < H; ++y) {
+                        const bool on = ((cw[y >> 5] >> (y & 31)) & 1u) != 0u;
+                        if (u8) d[y] = on ? 1 : 0;
+                        else reinterpret_cast<float *>(d)[y] = on ? 1.0f : 0.0f;
+                    }
                 }
             }
-        } else {
-            for (int it = lane; it < items; it += 32) {
-                const int r = WCT ? it / W : (int)(((uint32_t)it * p.inv_w20) >> 20);
-                const int x = it - r * W;
-                const uint32_t *cw = recs + r * pitch + kStateWords + CW * x;
-                for (int y = 0; y < H; ++y) {
-                    const bool on = ((cw[y >> 5] >> (y & 31)) & 1u) != 0u;
-                    if (u8) stage[it * H + y] = on ? 1 : 0;
-                    else reinterpret_cast<float *>(stage)[it * H + y] = on ? 1.0f : 0.0f;
-                }
-            }
-        }
-        unsigned char *dst = reinterpret_cast<unsigned char *>(p.obs) +
-                             ((long long)t * p.obs_t_stride + e0 * (long long)p.obs_elems) * (u8 ? 1 : 4);
-        const uint32_t bytes = (uint32_t)(nvalid * nel * (u8 ? 1 : 4));
-        if (((reinterpret_cast<uintptr_t>(dst) | bytes) & 15) == 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // every lane: its staging writes, for the TMA engine
+            const uint32_t bytes = (uint32_t)((items - it0 < 32 ? items - it0 : 32) * item_bytes);
+            unsigned char *dst = dstb + (size_t)it0 * item_bytes;
+            const bool bulk = ((reinterpret_cast<uintptr_t>(dst) | bytes) & 15) == 0;
+            if (bulk) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // every lane: its chunk writes, for the TMA engine
             __syncwarp();
+            if (!bulk) {  // ragged tails of uint8 / odd-height batches: plain stores from the chunk buffer
+                if (((reinterpret_cast<uintptr_t>(dst) | bytes) & 3) == 0)
+                    for (uint32_t i = lane; i < (bytes >> 2); i += 32) reinterpret_cast<uint32_t *>(dst)[i] = reinterpret_cast<const uint32_t *>(buf)[i];
+                else
+                    for (uint32_t i = lane; i < bytes; i += 32) dst[i] = buf[i];
+                __syncwarp();
+            }
             if (lane == 0) {
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(stage)), "r"(bytes) : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                if (bulk) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(buf)), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");  // one group per chunk, empty or not: the wait above counts groups
             }
-        } else {  // ragged tail of a uint8 batch / odd boards: plain stores from the staging block
-            __syncwarp();
-            if (((reinterpret_cast<uintptr_t>(dst) | bytes) & 3) == 0)
-                for (uint32_t i = lane; i < (bytes >> 2); i += 32) reinterpret_cast<uint32_t *>(dst)[i] = reinterpret_cast<const uint32_t *>(stage)[i];
-            else
-                for (uint32_t i = lane; i < bytes; i += 32) dst[i] = stage[i];
-            __syncwarp();
         }
     } else {
         __syncwarp();
@@ -780,12 +789,13 @@ struct TpeShape {
     int epw, wpc, ctas_per_sm, staged;
 };
 
-static size_t tpe_smem_bytes(const Params &p, int epw, int wpc, int staged)
+static size_t tpe_smem_bytes(const Params &p, int epw, int wpc, int staged, int nrec)
 {
     const int pitch = (p.stride >> 2) | 1;
     const int rec_words = (epw * pitch + 3) & ~3;
-    const int stage_words = staged ? (epw * p.W * p.H * (p.obs_u8 ? 1 : 4) + 15) >> 4 << 2 : (epw * (p.W * p.H >> 2) + 15) >> 4 << 2;
-    return (size_t)wpc * (2 * rec_words + stage_words) * 4;
+    const int chunk_bytes = (32 * p.H * (p.obs_u8 ? 1 : 4) + 15) & ~15;
+    const int stage_words = staged ? 2 * chunk_bytes >> 2 : (epw * (p.W * p.H >> 2) + 15) >> 4 << 2;
+    return (size_t)wpc * (nrec * rec_words + stage_words) * 4;
 }
 
 constexpr size_t kTpeSmemMax = 227 * 1024 - 1024;  // per CTA, minus the static tables and the per-CTA reserve
@@ -795,7 +805,7 @@ static cudaError_t launch_tpe_t(const Params &p, const TpeShape &s, cudaStream_t
 {
     const long long ngroups = (p.n + s.epw - 1) / s.epw;
     long long nctas = (ngroups + s.wpc - 1) / s.wpc;
-    const size_t smem = tpe_smem_bytes(p, s.epw, s.wpc, s.staged);
+    const size_t smem = tpe_smem_bytes(p, s.epw, s.wpc, s.staged, p.tpe_nrec);
     static const bool pdl = getenv("ST_B200_NO_PDL") == nullptr;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -860,9 +870,10 @@ static TpeShape tpe_shape(const Params &p)
     if (s.wpc != 1 && s.wpc != 2 && s.wpc != 4 && s.wpc != 8) s.wpc = 4;
     // boards whose columns are not whole float4s always go through the staging block
     s.staged = (p.H & 3) != 0 ? 1 : env_int("ST_B200_TPE_STAGED", 0);
-    while (s.wpc > 1 && tpe_smem_bytes(p, s.epw, s.wpc, s.staged) > kTpeSmemMax) s.wpc >>= 1;
-    while (s.epw > 4 && tpe_smem_bytes(p, s.epw, s.wpc, s.staged) > kTpeSmemMax) s.epw >>= 1;
     s.ctas_per_sm = env_int("ST_B200_TPE_CTAS_PER_SM", 0);
+    const int nrec = s.ctas_per_sm > 0 ? 2 : 1;
+    while (s.wpc > 1 && tpe_smem_bytes(p, s.epw, s.wpc, s.staged, nrec) > kTpeSmemMax) s.wpc >>= 1;
+    while (s.epw > 4 && tpe_smem_bytes(p, s.epw, s.wpc, s.staged, nrec) > kTpeSmemMax) s.epw >>= 1;
     return s;
 }
 
@@ -870,7 +881,7 @@ static TpeShape tpe_shape(const Params &p)
 static bool tpe_eligible(const Params &p, int obs_type)
 {
     return obs_type == 0 && p.mode == MODE_STEP && p.n > 0 && (p.obs_t_stride & 3) == 0 &&
-           tpe_smem_bytes(p, 4, 1, 1) <= kTpeSmemMax;
+           tpe_smem_bytes(p, 4, 1, 1, 2) <= kTpeSmemMax;
 }
 
 static cudaError_t launch_tpe(const Params &p0, cudaStream_t stream)
@@ -879,6 +890,7 @@ static cudaError_t launch_tpe(const Params &p0, cudaStream_t stream)
     const TpeShape s = tpe_shape(p);
     p.tpe_epw = s.epw;
     p.tpe_staged = s.staged;
+    p.tpe_nrec = s.ctas_per_sm > 0 ? 2 : 1;
     p.tpe_l2 = env_int("ST_B200_TPE_L2", 1);  // observations / info leave as evict_first streams (measured: -3..5 %)
 #if ST_TPE_TRACE
     static int launch_id = 0;

@@ -73,7 +73,7 @@ def algorithmic_bytes(kw, T=1):
     ot = kw.get("obs_type", "ram")
     esz = 1 if kw.get("obs_dtype") == "uint8" else 4
     obs = esz * (W * H if ot == "ram" else 84 * 84 * (3 if ot == "rgb" else 1))
-    state = 60 + H * (2 if W <= 16 else 4)
+    state = 60 + W * (4 if H <= 31 else 8)  # 15 words + one column word (two above 31 rows) per board column
     return obs + 6 + (2 * state if T == 1 else 2.0 * state / T)
 
 

@@ -48,7 +48,7 @@ __device__ __forceinline__ unsigned long long tpe_now()
 }
 #define TPE_MARK(slot)                                                                                        \
     do {                                                                                                      \
-        if (g_tpe_trace && lane == 0 && g == (long long)blockIdx.x * wpc + warp && (size_t)g < kTraceWarps)     \
+        if (g_tpe_trace && lane == 0 && g == (int)blockIdx.x * wpc + warp && (size_t)g < kTraceWarps)           \
             g_tpe_trace[((size_t)(p.draw_piece & 7) * kTraceWarps + (size_t)blockIdx.x * wpc + warp) * 16 + (slot)] = tpe_now(); \
     } while (0)
 #else
@@ -103,7 +103,9 @@ constexpr CellTab make_cell_tab()
     return t;
 }
 
-__constant__ CellTab c_cells = make_cell_tab();
+// read once per CTA into shared memory, one entry per thread: plain global memory (a lane-indexed __constant__
+// load would be replayed once per distinct address)
+__device__ const CellTab g_cells = make_cell_tab();
 
 template <typename ColT> struct ColOps;
 template <> struct ColOps<uint32_t> {
@@ -425,11 +427,11 @@ __device__ __forceinline__ void stg32(void *ptr, uint32_t v, unsigned long long 
 #endif
 
 // Records of one group: HBM -> shared memory, asynchronously (one cp.async group per call, possibly empty).
-__device__ __forceinline__ void tpe_fetch(uint32_t *recs, const unsigned char *state, long long e0, int nvalid, int SW, int pitch,
+__device__ __forceinline__ void tpe_fetch(uint32_t *recs, const unsigned char *state, int e0, int nvalid, int SW, int pitch,
                                           int stride, uint32_t inv_sw20, int lane, unsigned long long pol)
 {
     if (nvalid > 0) {
-        const uint32_t *g_rec = reinterpret_cast<const uint32_t *>(state + e0 * (long long)stride);
+        const uint32_t *g_rec = reinterpret_cast<const uint32_t *>(state + (long long)e0 * stride);
         const int nwords = nvalid * SW;
 #if ST_TPE_NO_CPASYNC
         if (pitch == SW && (reinterpret_cast<uintptr_t>(g_rec) & 15) == 0) {
@@ -454,9 +456,113 @@ __device__ __forceinline__ void tpe_fetch(uint32_t *recs, const unsigned char *s
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
+// Observations of one group by direct 16-byte stores (float32 [W][H] per env, ref:421-424, 400; needs H % 4 == 0 — the
+// launcher stages everything else).  Two passes, each with the lane mapping that makes its addressing trivial:
+//  a. one lane per (env, column): the column's H / 4 nibbles go into a byte array in slot order — (env, column) pairs
+//     and the float4 slots of a column are both consecutive in the group's block — as table OFFSETS (and, for the
+//     speculative store, the column words themselves into `shadow`);
+//  b. one lane per float4 slot: byte -> table entry -> store, 512 contiguous bytes per warp instruction, four
+//     independent stores in flight per lane (a store holds its source registers until the LSU has read them).
+template <typename ColT, int WCT, int HCT>
+__device__ __forceinline__ void tpe_obs_direct(const uint32_t *recs, unsigned char *stage, uint32_t *shadow, unsigned char *dst,
+                                            const float4 *s_lut, int nvalid, int Wrt, int Hrt, int pitch, uint32_t inv_w20, bool u8,
+                                            int lane, unsigned long long pol_out)
+{
+    constexpr int CW = ColOps<ColT>::kWords;
+    const int W = WCT ? WCT : Wrt, H = HCT ? HCT : Hrt;
+    const int hq = H >> 2, nq = W * hq, total = nvalid * nq, items = nvalid * W;
+    for (int it = lane; it < items; it += 32) {
+        const int r = WCT ? (int)((unsigned)it / (unsigned)W) : (int)(((uint32_t)it * inv_w20) >> 20);
+        const int x = it - r * W;
+        const uint32_t *cw = recs + r * pitch + kStateWords + CW * x;
+        unsigned char *d = stage + it * hq;
+        if constexpr (CW == 1) {
+            const uint32_t c0 = cw[0];
+            if (shadow) shadow[it] = c0;
+            const uint32_t w = c0 << 4;
+#pragma unroll
+            for (int k = 0; k < hq; ++k) d[k] = (unsigned char)((w >> (4 * k)) & 0xf0u);
+        } else {
+            const uint32_t c0 = cw[0], c1 = cw[1];
+            if (shadow) { shadow[2 * it] = c0; shadow[2 * it + 1] = c1; }
+            const unsigned long long w = ((unsigned long long)c1 << 32) | c0;
+#pragma unroll
+            for (int k = 0; k < hq; ++k) d[k] = (unsigned char)(((w >> (4 * k)) & 15u) << 4);
+        }
+    }
+    __syncwarp();
+    if (!u8) {
+        // whole rounds of 4 x 32 slots: no clamps, no predicates, every offset an immediate of one running pointer
+        const unsigned char *sp = stage + lane;
+        float4 *dp = reinterpret_cast<float4 *>(dst) + lane;
+        const int nfull = total & ~127;
+        for (int base = 0; base < nfull; base += 128, sp += 128, dp += 128) {
+            uint32_t off[4];
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) off[u] = sp[32 * u];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(s_lut) + off[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) stg128(dp + 32 * u, v[u], pol_out);
+        }
+        if (nfull < total) {  // the last, partial round: clamped loads, predicated stores
+            uint32_t off[4];
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) off[u] = stage[min(nfull + lane + 32 * u, total - 1)];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(s_lut) + off[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (nfull + lane + 32 * u < total) stg128(dp + 32 * u, v[u], pol_out);
+        }
+    } else {
+        for (int s4 = lane; s4 < total; s4 += 32)
+            stg32(reinterpret_cast<uint32_t *>(dst) + s4, (((uint32_t)stage[s4] >> 4) * 0x00204081u) & 0x01010101u, pol_out);
+    }
+}
+
+// Speculative observations (float32, direct stores): the board as the step FOUND it went out with tpe_obs_direct before
+// the engine ran — a step changes a handful of cells (the piece moves; one step in five..eight it locks; a line clear
+// or a reset is rarer still), and the store pipe, which is what a single-step launch ends up waiting for, would
+// otherwise idle until the engine is done.  Afterwards one lane per (env, column) compares what the observation must
+// show (`recs`: board + piece overlay, or the empty board of an auto-reset) with what was sent (`shadow`) and rewrites
+// the float4 slots whose cells differ.  The rewrite is ordered after the first store of the same address by the
+// __syncwarp()s in between (program order within the warp).
+template <typename ColT, int WCT>
+__device__ __forceinline__ void tpe_obs_fixup(const uint32_t *recs, const uint32_t *shadow, unsigned char *dst, const float4 *s_lut,
+                                              int nvalid, int W, int H, int pitch, uint32_t inv_w20, int lane, unsigned long long pol_out)
+{
+    constexpr int CW = ColOps<ColT>::kWords;
+    const int hq = H >> 2, items = nvalid * W;
+    for (int it = lane; it < items; it += 32) {
+        const int r = WCT ? (int)((unsigned)it / (unsigned)W) : (int)(((uint32_t)it * inv_w20) >> 20);
+        const int x = it - r * W;
+        const uint32_t *cw = recs + r * pitch + kStateWords + CW * x;
+        float4 *d = reinterpret_cast<float4 *>(dst) + it * hq;
+        if constexpr (CW == 1) {
+            const uint32_t cur = cw[0], diff = cur ^ shadow[it];
+            if (diff) {
+#pragma unroll
+                for (int k = 0; k < hq; ++k)
+                    if ((diff >> (4 * k)) & 15u) stg128(d + k, s_lut[(cur >> (4 * k)) & 15u], pol_out);
+            }
+        } else {
+            const unsigned long long cur = ((unsigned long long)cw[1] << 32) | cw[0];
+            const unsigned long long diff = cur ^ (((unsigned long long)shadow[2 * it + 1] << 32) | shadow[2 * it]);
+            if (diff) {
+#pragma unroll
+                for (int k = 0; k < hq; ++k)
+                    if ((diff >> (4 * k)) & 15u) stg128(d + k, s_lut[(cur >> (4 * k)) & 15u], pol_out);
+            }
+        }
+    }
+}
+
 // WCT / HCT: board size known at compile time (0 = taken from Params): the column loops unroll and the divisions by
 // W, H / 4 fold into constants for the boards every BASELINE.json workload uses.
-template <typename ColT, int WCT, int HCT>
+template <typename ColT, int WCT, int HCT, bool SPEC>
 __global__ void __launch_bounds__(32 * kTpeMaxWarps, ST_TPE_MINBLOCKS) st_step_tpe_kernel(const __grid_constant__ Params p)
 {
     extern __shared__ __align__(128) uint32_t s_dyn[];
@@ -469,7 +575,7 @@ __global__ void __launch_bounds__(32 * kTpeMaxWarps, ST_TPE_MINBLOCKS) st_step_t
     if (g_tpe_trace && lane == 0 && (size_t)blockIdx.x * wpc + warp < kTraceWarps)
         g_tpe_trace[((size_t)(p.draw_piece & 7) * kTraceWarps + (size_t)blockIdx.x * wpc + warp) * 16 + 9] = tpe_now();
 #endif
-    for (int i = threadIdx.x; i < 56; i += blockDim.x) s_cells[i] = i < 28 ? c_cells.e[i] : c_cells.c[i - 28];
+    for (int i = threadIdx.x; i < 56; i += blockDim.x) s_cells[i] = __ldg(reinterpret_cast<const unsigned long long *>(&g_cells) + i);
     if (threadIdx.x < 16)
         s_lut[threadIdx.x] = make_float4((threadIdx.x & 1) ? 1.0f : 0.0f, (threadIdx.x & 2) ? 1.0f : 0.0f,
                                          (threadIdx.x & 4) ? 1.0f : 0.0f, (threadIdx.x & 8) ? 1.0f : 0.0f);
@@ -484,13 +590,19 @@ __global__ void __launch_bounds__(32 * kTpeMaxWarps, ST_TPE_MINBLOCKS) st_step_t
     const bool staged = p.tpe_staged != 0;
     // staged: two chunk buffers of 32 (env, column) items; direct: one byte per float4 slot of the group's block
     const int chunk_bytes = (32 * H * (u8 ? 1 : 4) + 15) & ~15;
-    const int stage_words = staged ? 2 * chunk_bytes >> 2 : (epw * (nel >> 2) + 15) >> 4 << 2;
+    // direct: one byte per float4 slot of the group's block, then (speculative store) one shadow copy of every column
+    const int nib_words = (epw * (nel >> 2) + 15) >> 4 << 2;
+    const int stage_words = staged ? 2 * chunk_bytes >> 2 : nib_words + epw * W * CW;
+    constexpr bool spec = SPEC;  // the launcher: only with float32 observations through direct stores
     const int nrec = p.tpe_nrec;  // record buffers per warp: 2 when warps walk over several groups (next group in flight)
     uint32_t *const wbase = s_dyn + (size_t)warp * (nrec * rec_words + stage_words);
     unsigned char *const stage = reinterpret_cast<unsigned char *>(wbase + nrec * rec_words);
-    const long long ngroups = (p.n + epw - 1) / epw;
-    const long long gstride = (long long)gridDim.x * wpc;
-    long long g = (long long)blockIdx.x * wpc + warp;
+    uint32_t *const shadow = wbase + nrec * rec_words + nib_words;
+    const int n32 = (int)p.n;  // launch_tpe refuses batches beyond 2^30 envs
+    const int epw_log2 = 31 - __clz(epw);
+    const int ngroups = (n32 + epw - 1) >> epw_log2;
+    const int gstride = (int)gridDim.x * wpc;
+    int g = (int)blockIdx.x * wpc + warp;
     __syncthreads();  // s_cells, s_lut
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (g >= ngroups) return;
@@ -500,22 +612,22 @@ __global__ void __launch_bounds__(32 * kTpeMaxWarps, ST_TPE_MINBLOCKS) st_step_t
     const size_t n_envs = (size_t)p.n;
     const unsigned long long pol_out = l2_policy((p.tpe_l2 & 1) ? 1 : 0), pol_state = l2_policy((p.tpe_l2 & 2) ? 2 : 0);
     if (nrec == 2) {
-        const long long e0 = g * epw;
-        const int nv = (int)(p.n - e0 < epw ? p.n - e0 : epw);
+        const int e0 = g << epw_log2;
+        const int nv = min(n32 - e0, epw);
         tpe_fetch(wbase, p.state, e0, nv, SW, pitch, p.stride, p.inv_sw20, lane, pol_state);
     }
     int cur = 0, chunk = 0;
     for (; g < ngroups; g += gstride, cur ^= nrec - 1) {
     uint32_t *const recs = wbase + cur * rec_words;
-    const long long e0 = g * epw;
-    const int nvalid = (int)(p.n - e0 < epw ? p.n - e0 : epw);
-    const long long e = e0 + lane;
+    const int e0 = g << epw_log2;
+    const int nvalid = min(n32 - e0, epw);
+    const int e = e0 + lane;
     unsigned int action_u = 6u;  // issued before the wait so that its miss overlaps the record copy
     if (lane < nvalid) asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(action_u) : "l"(p.actions + e));
     if (nrec == 2) {  // 1. next group's records on their way; this group's have arrived
-        const long long gn = g + gstride;
-        const long long en = gn * epw;
-        const int nvn = gn < ngroups ? (int)(p.n - en < epw ? p.n - en : epw) : 0;
+        const int gn = g + gstride;
+        const int en = gn << epw_log2;
+        const int nvn = gn < ngroups ? min(n32 - en, epw) : 0;
         tpe_fetch(wbase + (cur ^ 1) * rec_words, p.state, en, nvn, SW, pitch, p.stride, p.inv_sw20, lane, pol_state);
         asm volatile("cp.async.wait_group 1;" ::: "memory");
     } else {
@@ -527,6 +639,10 @@ __global__ void __launch_bounds__(32 * kTpeMaxWarps, ST_TPE_MINBLOCKS) st_step_t
 
     const TpeRec<ColT> rec = {recs + lane * pitch};
     for (int t = 0; t < p.T; ++t) {  // st_step_many: the records stay in shared memory between steps
+    if constexpr (spec) {  // the board as this step finds it goes out now (no piece on it: ref:303); step 4 rewrites what changed
+        unsigned char *dst = reinterpret_cast<unsigned char *>(p.obs) + ((long long)t * p.obs_t_stride + (long long)e0 * p.obs_elems) * 4;
+        tpe_obs_direct<ColT, WCT, HCT>(recs, stage, shadow, dst, s_lut, nvalid, W, H, pitch, p.inv_w20, false, lane, pol_out);
+    }
     // 2. engine, one env per lane
     int reward = 0, done = 0;
     if (lane < nvalid) tpe_engine_step(rec, (int)action_u, p, W, H, e, s_cells, reward, done, errbits);
@@ -537,7 +653,7 @@ __global__ void __launch_bounds__(32 * kTpeMaxWarps, ST_TPE_MINBLOCKS) st_step_t
 
     if (p.term_obs) {  // terminal observation of the envs that end here: their board already holds the locked piece
         unsigned term = __ballot_sync(FULL, lane < nvalid && done && p.auto_reset);
-        char *tb = reinterpret_cast<char *>(p.term_obs) + ((long long)t * p.obs_t_stride + e0 * (long long)p.obs_elems) * (u8 ? 1 : 4);
+        char *tb = reinterpret_cast<char *>(p.term_obs) + ((long long)t * p.obs_t_stride + (long long)e0 * p.obs_elems) * (u8 ? 1 : 4);
         while (term) {
             const int r = __ffs((int)term) - 1;
             term &= term - 1;
@@ -596,50 +712,10 @@ __global__ void __launch_bounds__(32 * kTpeMaxWarps, ST_TPE_MINBLOCKS) st_step_t
     // 4. observations: float32 [W][H] per env (ref:421-424, 400).  One lane per (env, column): the column's cells are
     //    consecutive in the observation, (env, column) pairs are consecutive in the group's block.
     if (p.obs && !staged) {
-        // direct 16-byte stores; needs H % 4 == 0 (the launcher stages everything else).  Two passes, each with the
-        // lane mapping that makes its addressing trivial:
-        //  a. one lane per (env, column): the column's H / 4 nibbles go into a byte array in slot order — (env, column)
-        //     pairs and the float4 slots of a column are both consecutive in the group's block — as table OFFSETS;
-        //  b. one lane per float4 slot: byte -> table entry -> store, 512 contiguous bytes per warp instruction, with
-        //     U independent stores in flight per lane (a store holds its source registers until the LSU has read them)
-        const int hq = H >> 2, nq = W * hq, total = nvalid * nq, items = nvalid * W;
-        for (int it = lane; it < items; it += 32) {
-            const int r = WCT ? (int)((unsigned)it / (unsigned)W) : (int)(((uint32_t)it * p.inv_w20) >> 20);
-            const int x = it - r * W;
-            const uint32_t *cw = recs + r * pitch + kStateWords + CW * x;
-            unsigned char *d = stage + it * hq;
-            if constexpr (CW == 1) {
-                const uint32_t w = cw[0] << 4;
-#pragma unroll
-                for (int k = 0; k < hq; ++k) d[k] = (unsigned char)((w >> (4 * k)) & 0xf0u);
-            } else {
-                const unsigned long long w = ((unsigned long long)cw[1] << 32) | cw[0];
-#pragma unroll
-                for (int k = 0; k < hq; ++k) d[k] = (unsigned char)(((w >> (4 * k)) & 15u) << 4);
-            }
-        }
-        __syncwarp();
         unsigned char *dst = reinterpret_cast<unsigned char *>(p.obs) +
-                             ((long long)t * p.obs_t_stride + e0 * (long long)p.obs_elems) * (u8 ? 1 : 4);
-        constexpr int U = 4;
-        for (int base = lane; base < total; base += 32 * U) {
-            uint32_t off[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) off[u] = stage[min(base + 32 * u, total - 1)];  // clamped: only the stores are predicated
-            if (!u8) {
-                float4 v[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) v[u] = *reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(s_lut) + off[u]);
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-                    if (base + 32 * u < total) stg128(reinterpret_cast<float4 *>(dst) + base + 32 * u, v[u], pol_out);
-            } else {
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-                    if (base + 32 * u < total)
-                        stg32(reinterpret_cast<uint32_t *>(dst) + base + 32 * u, ((off[u] >> 4) * 0x00204081u) & 0x01010101u, pol_out);
-            }
-        }
+                             ((long long)t * p.obs_t_stride + (long long)e0 * p.obs_elems) * (u8 ? 1 : 4);
+        if constexpr (spec) tpe_obs_fixup<ColT, WCT>(recs, shadow, dst, s_lut, nvalid, W, H, pitch, p.inv_w20, lane, pol_out);
+        else tpe_obs_direct<ColT, WCT, HCT>(recs, stage, nullptr, dst, s_lut, nvalid, W, H, pitch, p.inv_w20, u8, lane, pol_out);
         __syncwarp();
     } else if (p.obs) {
         // staged: 32 (env, column) items at a time — H consecutive cells each, and consecutive items are consecutive
@@ -649,7 +725,7 @@ __global__ void __launch_bounds__(32 * kTpeMaxWarps, ST_TPE_MINBLOCKS) st_step_t
         const int items = nvalid * W;
         const int item_bytes = H * (u8 ? 1 : 4);
         unsigned char *dstb = reinterpret_cast<unsigned char *>(p.obs) +
-                              ((long long)t * p.obs_t_stride + e0 * (long long)p.obs_elems) * (u8 ? 1 : 4);
+                              ((long long)t * p.obs_t_stride + (long long)e0 * p.obs_elems) * (u8 ? 1 : 4);
         for (int it0 = 0; it0 < items; it0 += 32, chunk ^= 1) {
             unsigned char *buf = stage + chunk * chunk_bytes;
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // the store of two chunks ago has read `buf`
@@ -703,21 +779,29 @@ __global__ void __launch_bounds__(32 * kTpeMaxWarps, ST_TPE_MINBLOCKS) st_step_t
     TPE_MARK(5);
     // 5. info: the counters as the step left them, before any reset (reward and done went out before the observation)
     if (p.info) {
-        int32_t *g_info = p.info + (long long)t * p.info_t_stride + e0 * kStateWords;
+        int32_t *g_info = p.info + (long long)t * p.info_t_stride + (long long)e0 * kStateWords;
         const int ninfo = nvalid * kStateWords;
-        for (int base = lane; base < ninfo; base += 128) {
-            uint32_t v[4];
+        if (((reinterpret_cast<uintptr_t>(g_info) & 15) | (nvalid & 3)) == 0) {
+            // 16-byte stores: the four words of slot q are words 4q..4q+3 of the group's [nvalid][15] block, i.e. word
+            // c, c+1, .. of record r = 4q / 15, running over into record r + 1 past word 14
+            for (int q = lane; q < (ninfo >> 2); q += 32) {
+                const int r = (q * 4 * 4370) >> 16;  // 4q / 15 for 4q < 480
+                const int c = 4 * q - r * kStateWords;
+                const uint32_t *src = recs + r * pitch + c;
+                uint32_t v[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int j = min(base + 32 * u, ninfo - 1);
+                for (int k = 0; k < 4; ++k) v[k] = src[c + k >= kStateWords ? k + pitch - kStateWords : k];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = (c + k == 0 || c + k == kStateWords) ? (v[k] & 15u) : v[k];  // word 0: the piece id only
+                stg128(reinterpret_cast<uint4 *>(g_info) + q, make_uint4(v[0], v[1], v[2], v[3]), pol_out);
+            }
+        } else {
+            for (int j = lane; j < ninfo; j += 32) {
                 const int r = (j * 4370) >> 16;  // j / 15 for j < 480
                 const int c = j - r * kStateWords;
-                v[u] = recs[r * pitch + c];
-                v[u] = c == 0 ? (v[u] & 15u) : v[u];
+                const uint32_t v = recs[r * pitch + c];
+                stg32(g_info + j, c == 0 ? (v & 15u) : v, pol_out);
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (base + 32 * u < ninfo) stg32(g_info + base + 32 * u, v[u], pol_out);
         }
     }
     __syncwarp();
@@ -747,18 +831,12 @@ __global__ void __launch_bounds__(32 * kTpeMaxWarps, ST_TPE_MINBLOCKS) st_step_t
     __syncwarp();
     }  // for t
     {   // records back to HBM
-        uint32_t *g_rec = reinterpret_cast<uint32_t *>(p.state + e0 * (long long)p.stride);
+        uint32_t *g_rec = reinterpret_cast<uint32_t *>(p.state + (long long)e0 * p.stride);
         const int nwords = nvalid * SW;
         if (pitch == SW && (reinterpret_cast<uintptr_t>(g_rec) & 15) == 0) {
             const int nvec = nwords >> 2;
-            for (int base = lane; base < nvec; base += 128) {
-                uint4 v[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = reinterpret_cast<const uint4 *>(recs)[min(base + 32 * u, nvec - 1)];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (base + 32 * u < nvec) stg128(reinterpret_cast<uint4 *>(g_rec) + base + 32 * u, v[u], pol_state);
-            }
+#pragma unroll 4
+            for (int i = lane; i < nvec; i += 32) stg128(reinterpret_cast<uint4 *>(g_rec) + i, reinterpret_cast<const uint4 *>(recs)[i], pol_state);
             for (int i = (nvec << 2) + lane; i < nwords; i += 32) g_rec[i] = recs[i];
         } else {
             for (int i = lane; i < nwords; i += 32) {
@@ -794,13 +872,13 @@ static size_t tpe_smem_bytes(const Params &p, int epw, int wpc, int staged, int 
     const int pitch = (p.stride >> 2) | 1;
     const int rec_words = (epw * pitch + 3) & ~3;
     const int chunk_bytes = (32 * p.H * (p.obs_u8 ? 1 : 4) + 15) & ~15;
-    const int stage_words = staged ? 2 * chunk_bytes >> 2 : (epw * (p.W * p.H >> 2) + 15) >> 4 << 2;
+    const int stage_words = staged ? 2 * chunk_bytes >> 2 : ((epw * (p.W * p.H >> 2) + 15) >> 4 << 2) + epw * p.W * p.col_words;
     return (size_t)wpc * (nrec * rec_words + stage_words) * 4;
 }
 
 constexpr size_t kTpeSmemMax = 227 * 1024 - 1024;  // per CTA, minus the static tables and the per-CTA reserve
 
-template <typename ColT, int WCT, int HCT>
+template <typename ColT, int WCT, int HCT, bool SPEC>
 static cudaError_t launch_tpe_t(const Params &p, const TpeShape &s, cudaStream_t stream)
 {
     const long long ngroups = (p.n + s.epw - 1) / s.epw;
@@ -812,7 +890,7 @@ static cudaError_t launch_tpe_t(const Params &p, const TpeShape &s, cudaStream_t
     static bool attr_set[64] = {};
     static int n_sm[64] = {};
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(st_step_tpe_kernel<ColT, WCT, HCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTpeSmemMax);
+        cudaError_t e = cudaFuncSetAttribute(st_step_tpe_kernel<ColT, WCT, HCT, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTpeSmemMax);
         if (e != cudaSuccess) return e;
         cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev);
         attr_set[dev] = true;
@@ -832,7 +910,7 @@ static cudaError_t launch_tpe_t(const Params &p, const TpeShape &s, cudaStream_t
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     count_launch();
-    return cudaLaunchKernelEx(&cfg, st_step_tpe_kernel<ColT, WCT, HCT>, p);
+    return cudaLaunchKernelEx(&cfg, st_step_tpe_kernel<ColT, WCT, HCT, SPEC>, p);
 }
 
 // Which batches take this kernel and with how many envs per group: measured on B200 (tools/knob_sweep.py, profiles/
@@ -880,7 +958,7 @@ static TpeShape tpe_shape(const Params &p)
 // Thread-per-env path: ram observations, single-step launches and st_step_many alike.
 static bool tpe_eligible(const Params &p, int obs_type)
 {
-    return obs_type == 0 && p.mode == MODE_STEP && p.n > 0 && (p.obs_t_stride & 3) == 0 &&
+    return obs_type == 0 && p.mode == MODE_STEP && p.n > 0 && p.n <= (1ll << 30) && (p.obs_t_stride & 3) == 0 &&
            tpe_smem_bytes(p, 4, 1, 1, 2) <= kTpeSmemMax;
 }
 
@@ -891,17 +969,19 @@ static cudaError_t launch_tpe(const Params &p0, cudaStream_t stream)
     p.tpe_epw = s.epw;
     p.tpe_staged = s.staged;
     p.tpe_nrec = s.ctas_per_sm > 0 ? 2 : 1;
+    p.tpe_spec = env_int("ST_B200_TPE_SPEC", 0);  // speculative observation store + fix-up: measured 40-60 % SLOWER (profiles/r2_tpe_speculative_store_ab.txt)
     p.tpe_l2 = env_int("ST_B200_TPE_L2", 1);  // observations / info leave as evict_first streams (measured: -3..5 %)
 #if ST_TPE_TRACE
     static int launch_id = 0;
     p.draw_piece = launch_id++;  // unused by step launches: which of the 8 trace slabs this launch writes
 #endif
+    const bool spec = p.tpe_spec != 0 && p.obs != nullptr && !s.staged && !p.obs_u8;
     if (p.col_words == 1) {
-        if (p.W == 10 && p.H == 20) return launch_tpe_t<uint32_t, 10, 20>(p, s, stream);
-        return launch_tpe_t<uint32_t, 0, 0>(p, s, stream);
+        if (p.W == 10 && p.H == 20) return spec ? launch_tpe_t<uint32_t, 10, 20, true>(p, s, stream) : launch_tpe_t<uint32_t, 10, 20, false>(p, s, stream);
+        return spec ? launch_tpe_t<uint32_t, 0, 0, true>(p, s, stream) : launch_tpe_t<uint32_t, 0, 0, false>(p, s, stream);
     }
-    if (p.W == 20 && p.H == 40) return launch_tpe_t<unsigned long long, 20, 40>(p, s, stream);
-    return launch_tpe_t<unsigned long long, 0, 0>(p, s, stream);
+    if (p.W == 20 && p.H == 40) return spec ? launch_tpe_t<unsigned long long, 20, 40, true>(p, s, stream) : launch_tpe_t<unsigned long long, 20, 40, false>(p, s, stream);
+    return spec ? launch_tpe_t<unsigned long long, 0, 0, true>(p, s, stream) : launch_tpe_t<unsigned long long, 0, 0, false>(p, s, stream);
 }
 
 }  // namespace st

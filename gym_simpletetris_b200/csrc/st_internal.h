@@ -58,7 +58,7 @@ struct Params {
     int tpe_l2;      // thread-per-env kernel: L2 eviction hints (bit 0: outputs evict_first, bit 1: records evict_last)
     int tpe_nrec;    // thread-per-env kernel: record buffers per warp (2 = next group prefetched; capped grids)
     int tpe_staged;  // thread-per-env kernel: observations through a shared-memory block + TMA bulk store
-    int tpe_spec;    // thread-per-env kernel: the board goes out before the engine runs, changed slots are rewritten after
+    int tpe_sync;    // thread-per-env kernel: CTA barrier between the engine and the store phases (one CTA per SM)
 };
 
 cudaError_t launch_main(const Params &p, int obs_type, cudaStream_t stream);

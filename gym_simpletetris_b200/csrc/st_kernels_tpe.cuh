@@ -29,9 +29,9 @@
 namespace st {
 
 #ifndef ST_TPE_MINBLOCKS
-#define ST_TPE_MINBLOCKS 4  // 256-thread CTAs x 4 = 64 registers per thread: 32 resident warps per SM
+#define ST_TPE_MINBLOCKS 1  // 1024-thread CTAs x 1 = 64 registers per thread: 32 resident warps per SM
 #endif
-constexpr int kTpeMaxWarps = 8;  // warps per CTA is a launch-time choice (1, 2, 4 or 8)
+constexpr int kTpeMaxWarps = 32;  // warps per CTA is a launch-time choice (1..32)
 
 // Phase timestamps of every warp (profiling builds only: -DST_TPE_TRACE=1, tools/tpe_trace.py)
 #ifndef ST_TPE_TRACE
@@ -426,6 +426,12 @@ __device__ __forceinline__ void stg32(void *ptr, uint32_t v, unsigned long long 
 }
 #endif
 
+// nibble << 4 -> four float32 cells (ref:400)
+__device__ __forceinline__ float4 tpe_slot(const float4 *s_lut, uint32_t off)
+{
+    return *reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(s_lut) + off);
+}
+
 // Records of one group: HBM -> shared memory, asynchronously (one cp.async group per call, possibly empty).
 __device__ __forceinline__ void tpe_fetch(uint32_t *recs, const unsigned char *state, int e0, int nvalid, int SW, int pitch,
                                           int stride, uint32_t inv_sw20, int lane, unsigned long long pol)
@@ -459,12 +465,11 @@ __device__ __forceinline__ void tpe_fetch(uint32_t *recs, const unsigned char *s
 // Observations of one group by direct 16-byte stores (float32 [W][H] per env, ref:421-424, 400; needs H % 4 == 0 — the
 // launcher stages everything else).  Two passes, each with the lane mapping that makes its addressing trivial:
 //  a. one lane per (env, column): the column's H / 4 nibbles go into a byte array in slot order — (env, column) pairs
-//     and the float4 slots of a column are both consecutive in the group's block — as table OFFSETS (and, for the
-//     speculative store, the column words themselves into `shadow`);
+//     and the float4 slots of a column are both consecutive in the group's block — as table OFFSETS;
 //  b. one lane per float4 slot: byte -> table entry -> store, 512 contiguous bytes per warp instruction, four
 //     independent stores in flight per lane (a store holds its source registers until the LSU has read them).
 template <typename ColT, int WCT, int HCT>
-__device__ __forceinline__ void tpe_obs_direct(const uint32_t *recs, unsigned char *stage, uint32_t *shadow, unsigned char *dst,
+__device__ __forceinline__ void tpe_obs_direct(const uint32_t *recs, unsigned char *stage, unsigned char *dst,
                                             const float4 *s_lut, int nvalid, int Wrt, int Hrt, int pitch, uint32_t inv_w20, bool u8,
                                             int lane, unsigned long long pol_out)
 {
@@ -478,13 +483,11 @@ __device__ __forceinline__ void tpe_obs_direct(const uint32_t *recs, unsigned ch
         unsigned char *d = stage + it * hq;
         if constexpr (CW == 1) {
             const uint32_t c0 = cw[0];
-            if (shadow) shadow[it] = c0;
             const uint32_t w = c0 << 4;
 #pragma unroll
             for (int k = 0; k < hq; ++k) d[k] = (unsigned char)((w >> (4 * k)) & 0xf0u);
         } else {
             const uint32_t c0 = cw[0], c1 = cw[1];
-            if (shadow) { shadow[2 * it] = c0; shadow[2 * it + 1] = c1; }
             const unsigned long long w = ((unsigned long long)c1 << 32) | c0;
 #pragma unroll
             for (int k = 0; k < hq; ++k) d[k] = (unsigned char)(((w >> (4 * k)) & 15u) << 4);
@@ -502,7 +505,7 @@ __device__ __forceinline__ void tpe_obs_direct(const uint32_t *recs, unsigned ch
 #pragma unroll
             for (int u = 0; u < 4; ++u) off[u] = sp[32 * u];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(s_lut) + off[u]);
+            for (int u = 0; u < 4; ++u) v[u] = tpe_slot(s_lut, off[u]);
 #pragma unroll
             for (int u = 0; u < 4; ++u) stg128(dp + 32 * u, v[u], pol_out);
         }
@@ -512,7 +515,7 @@ __device__ __forceinline__ void tpe_obs_direct(const uint32_t *recs, unsigned ch
 #pragma unroll
             for (int u = 0; u < 4; ++u) off[u] = stage[min(nfull + lane + 32 * u, total - 1)];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(s_lut) + off[u]);
+            for (int u = 0; u < 4; ++u) v[u] = tpe_slot(s_lut, off[u]);
 #pragma unroll
             for (int u = 0; u < 4; ++u)
                 if (nfull + lane + 32 * u < total) stg128(dp + 32 * u, v[u], pol_out);
@@ -523,46 +526,9 @@ __device__ __forceinline__ void tpe_obs_direct(const uint32_t *recs, unsigned ch
     }
 }
 
-// Speculative observations (float32, direct stores): the board as the step FOUND it went out with tpe_obs_direct before
-// the engine ran — a step changes a handful of cells (the piece moves; one step in five..eight it locks; a line clear
-// or a reset is rarer still), and the store pipe, which is what a single-step launch ends up waiting for, would
-// otherwise idle until the engine is done.  Afterwards one lane per (env, column) compares what the observation must
-// show (`recs`: board + piece overlay, or the empty board of an auto-reset) with what was sent (`shadow`) and rewrites
-// the float4 slots whose cells differ.  The rewrite is ordered after the first store of the same address by the
-// __syncwarp()s in between (program order within the warp).
-template <typename ColT, int WCT>
-__device__ __forceinline__ void tpe_obs_fixup(const uint32_t *recs, const uint32_t *shadow, unsigned char *dst, const float4 *s_lut,
-                                              int nvalid, int W, int H, int pitch, uint32_t inv_w20, int lane, unsigned long long pol_out)
-{
-    constexpr int CW = ColOps<ColT>::kWords;
-    const int hq = H >> 2, items = nvalid * W;
-    for (int it = lane; it < items; it += 32) {
-        const int r = WCT ? (int)((unsigned)it / (unsigned)W) : (int)(((uint32_t)it * inv_w20) >> 20);
-        const int x = it - r * W;
-        const uint32_t *cw = recs + r * pitch + kStateWords + CW * x;
-        float4 *d = reinterpret_cast<float4 *>(dst) + it * hq;
-        if constexpr (CW == 1) {
-            const uint32_t cur = cw[0], diff = cur ^ shadow[it];
-            if (diff) {
-#pragma unroll
-                for (int k = 0; k < hq; ++k)
-                    if ((diff >> (4 * k)) & 15u) stg128(d + k, s_lut[(cur >> (4 * k)) & 15u], pol_out);
-            }
-        } else {
-            const unsigned long long cur = ((unsigned long long)cw[1] << 32) | cw[0];
-            const unsigned long long diff = cur ^ (((unsigned long long)shadow[2 * it + 1] << 32) | shadow[2 * it]);
-            if (diff) {
-#pragma unroll
-                for (int k = 0; k < hq; ++k)
-                    if ((diff >> (4 * k)) & 15u) stg128(d + k, s_lut[(cur >> (4 * k)) & 15u], pol_out);
-            }
-        }
-    }
-}
-
 // WCT / HCT: board size known at compile time (0 = taken from Params): the column loops unroll and the divisions by
 // W, H / 4 fold into constants for the boards every BASELINE.json workload uses.
-template <typename ColT, int WCT, int HCT, bool SPEC>
+template <typename ColT, int WCT, int HCT>
 __global__ void __launch_bounds__(32 * kTpeMaxWarps, ST_TPE_MINBLOCKS) st_step_tpe_kernel(const __grid_constant__ Params p)
 {
     extern __shared__ __align__(128) uint32_t s_dyn[];
@@ -590,14 +556,10 @@ __global__ void __launch_bounds__(32 * kTpeMaxWarps, ST_TPE_MINBLOCKS) st_step_t
     const bool staged = p.tpe_staged != 0;
     // staged: two chunk buffers of 32 (env, column) items; direct: one byte per float4 slot of the group's block
     const int chunk_bytes = (32 * H * (u8 ? 1 : 4) + 15) & ~15;
-    // direct: one byte per float4 slot of the group's block, then (speculative store) one shadow copy of every column
-    const int nib_words = (epw * (nel >> 2) + 15) >> 4 << 2;
-    const int stage_words = staged ? 2 * chunk_bytes >> 2 : nib_words + epw * W * CW;
-    constexpr bool spec = SPEC;  // the launcher: only with float32 observations through direct stores
+    const int stage_words = staged ? 2 * chunk_bytes >> 2 : (epw * (nel >> 2) + 15) >> 4 << 2;
     const int nrec = p.tpe_nrec;  // record buffers per warp: 2 when warps walk over several groups (next group in flight)
     uint32_t *const wbase = s_dyn + (size_t)warp * (nrec * rec_words + stage_words);
     unsigned char *const stage = reinterpret_cast<unsigned char *>(wbase + nrec * rec_words);
-    uint32_t *const shadow = wbase + nrec * rec_words + nib_words;
     const int n32 = (int)p.n;  // launch_tpe refuses batches beyond 2^30 envs
     const int epw_log2 = 31 - __clz(epw);
     const int ngroups = (n32 + epw - 1) >> epw_log2;
@@ -605,7 +567,10 @@ __global__ void __launch_bounds__(32 * kTpeMaxWarps, ST_TPE_MINBLOCKS) st_step_t
     int g = (int)blockIdx.x * wpc + warp;
     __syncthreads();  // s_cells, s_lut
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (g >= ngroups) return;
+    if (g >= ngroups) {
+        if (p.tpe_sync) __syncthreads();  // the phase barrier below counts every warp of the CTA
+        return;
+    }
     TPE_MARK(0);
 
     int errbits = 0;
@@ -639,10 +604,6 @@ __global__ void __launch_bounds__(32 * kTpeMaxWarps, ST_TPE_MINBLOCKS) st_step_t
 
     const TpeRec<ColT> rec = {recs + lane * pitch};
     for (int t = 0; t < p.T; ++t) {  // st_step_many: the records stay in shared memory between steps
-    if constexpr (spec) {  // the board as this step finds it goes out now (no piece on it: ref:303); step 4 rewrites what changed
-        unsigned char *dst = reinterpret_cast<unsigned char *>(p.obs) + ((long long)t * p.obs_t_stride + (long long)e0 * p.obs_elems) * 4;
-        tpe_obs_direct<ColT, WCT, HCT>(recs, stage, shadow, dst, s_lut, nvalid, W, H, pitch, p.inv_w20, false, lane, pol_out);
-    }
     // 2. engine, one env per lane
     int reward = 0, done = 0;
     if (lane < nvalid) tpe_engine_step(rec, (int)action_u, p, W, H, e, s_cells, reward, done, errbits);
@@ -707,6 +668,12 @@ __global__ void __launch_bounds__(32 * kTpeMaxWarps, ST_TPE_MINBLOCKS) st_step_t
     }
     TPE_MARK(3);
     __syncwarp();
+    // Experiment knob (ST_B200_TPE_SYNC=1, off): ONE CTA per SM and nobody stores before every warp of the SM has stepped
+    // its envs.  Stores and shared-memory loads share the LSU queue, so without the barrier the engines of late warps
+    // crawl behind the early warps' stores (engine done: p95 7.9 us, max 10.5 us at 65 536 envs; with the barrier 5.0 /
+    // 5.7 us).  But once every SM stores at the same time the stream runs at the HBM write rate (59 MB in 7.2 us), and
+    // the launch ends later than with the ragged overlap (16.7 against 14.7 us): profiles/r2_tpe_phase_barrier_ab.txt.
+    if (p.tpe_sync) __syncthreads();
     TPE_MARK(4);
 
     // 4. observations: float32 [W][H] per env (ref:421-424, 400).  One lane per (env, column): the column's cells are
@@ -714,8 +681,7 @@ __global__ void __launch_bounds__(32 * kTpeMaxWarps, ST_TPE_MINBLOCKS) st_step_t
     if (p.obs && !staged) {
         unsigned char *dst = reinterpret_cast<unsigned char *>(p.obs) +
                              ((long long)t * p.obs_t_stride + (long long)e0 * p.obs_elems) * (u8 ? 1 : 4);
-        if constexpr (spec) tpe_obs_fixup<ColT, WCT>(recs, shadow, dst, s_lut, nvalid, W, H, pitch, p.inv_w20, lane, pol_out);
-        else tpe_obs_direct<ColT, WCT, HCT>(recs, stage, nullptr, dst, s_lut, nvalid, W, H, pitch, p.inv_w20, u8, lane, pol_out);
+        tpe_obs_direct<ColT, WCT, HCT>(recs, stage, dst, s_lut, nvalid, W, H, pitch, p.inv_w20, u8, lane, pol_out);
         __syncwarp();
     } else if (p.obs) {
         // staged: 32 (env, column) items at a time — H consecutive cells each, and consecutive items are consecutive
@@ -864,21 +830,31 @@ __global__ void __launch_bounds__(32 * kTpeMaxWarps, ST_TPE_MINBLOCKS) st_step_t
 
 // Launch shape of the thread-per-env kernel: envs per group, warps per CTA, grid cap (CTAs per SM; 0 = one group per warp).
 struct TpeShape {
-    int epw, wpc, ctas_per_sm, staged;
+    int epw, wpc, ctas_per_sm, staged, sync;
 };
+
+static int tpe_sm_count()
+{
+    static int n_sm[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 148;
+    if (!n_sm[dev]) cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev);
+    return n_sm[dev] > 0 ? n_sm[dev] : 148;
+}
 
 static size_t tpe_smem_bytes(const Params &p, int epw, int wpc, int staged, int nrec)
 {
     const int pitch = (p.stride >> 2) | 1;
     const int rec_words = (epw * pitch + 3) & ~3;
     const int chunk_bytes = (32 * p.H * (p.obs_u8 ? 1 : 4) + 15) & ~15;
-    const int stage_words = staged ? 2 * chunk_bytes >> 2 : ((epw * (p.W * p.H >> 2) + 15) >> 4 << 2) + epw * p.W * p.col_words;
+    const int stage_words = staged ? 2 * chunk_bytes >> 2 : (epw * (p.W * p.H >> 2) + 15) >> 4 << 2;
     return (size_t)wpc * (nrec * rec_words + stage_words) * 4;
 }
 
 constexpr size_t kTpeSmemMax = 227 * 1024 - 1024;  // per CTA, minus the static tables and the per-CTA reserve
 
-template <typename ColT, int WCT, int HCT, bool SPEC>
+template <typename ColT, int WCT, int HCT>
 static cudaError_t launch_tpe_t(const Params &p, const TpeShape &s, cudaStream_t stream)
 {
     const long long ngroups = (p.n + s.epw - 1) / s.epw;
@@ -890,7 +866,7 @@ static cudaError_t launch_tpe_t(const Params &p, const TpeShape &s, cudaStream_t
     static bool attr_set[64] = {};
     static int n_sm[64] = {};
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(st_step_tpe_kernel<ColT, WCT, HCT, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTpeSmemMax);
+        cudaError_t e = cudaFuncSetAttribute(st_step_tpe_kernel<ColT, WCT, HCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTpeSmemMax);
         if (e != cudaSuccess) return e;
         cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev);
         attr_set[dev] = true;
@@ -910,7 +886,7 @@ static cudaError_t launch_tpe_t(const Params &p, const TpeShape &s, cudaStream_t
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     count_launch();
-    return cudaLaunchKernelEx(&cfg, st_step_tpe_kernel<ColT, WCT, HCT, SPEC>, p);
+    return cudaLaunchKernelEx(&cfg, st_step_tpe_kernel<ColT, WCT, HCT>, p);
 }
 
 // Which batches take this kernel and with how many envs per group: measured on B200 (tools/knob_sweep.py, profiles/
@@ -945,11 +921,28 @@ static TpeShape tpe_shape(const Params &p)
     s.epw = env_int("ST_B200_TPE_EPW", tpe_default_epw(p));
     if (s.epw != 4 && s.epw != 8 && s.epw != 16 && s.epw != 32) s.epw = 32;
     s.wpc = env_int("ST_B200_TPE_WPC", 4);
-    if (s.wpc != 1 && s.wpc != 2 && s.wpc != 4 && s.wpc != 8) s.wpc = 4;
+    if (s.wpc < 1 || s.wpc > kTpeMaxWarps) s.wpc = 4;
+    // Experiment (off): single-step launches whose groups fit the machine in one wave as ONE CTA per SM with a barrier
+    // between the engine and the store phases (see the kernel; measured slower, profiles/r2_tpe_phase_barrier_ab.txt).
+    s.sync = 0;
+    {
+        const long long ngroups = (p.n + s.epw - 1) / s.epw;
+        const int n_sm = tpe_sm_count();
+        const long long per_sm = (ngroups + n_sm - 1) / n_sm;
+        const int want = env_int("ST_B200_TPE_SYNC", 0);
+        if (want && p.T == 1 && per_sm <= kTpeMaxWarps && per_sm >= env_int("ST_B200_TPE_SYNC_MIN", 8) && getenv("ST_B200_TPE_WPC") == nullptr &&
+            getenv("ST_B200_TPE_CTAS_PER_SM") == nullptr) {
+            s.wpc = (int)per_sm;
+            s.sync = 1;
+        } else if (want == 2 && p.T == 1) {
+            s.sync = 1;  // experiment: barrier with whatever CTA shape was asked for
+        }
+    }
     // boards whose columns are not whole float4s always go through the staging block
     s.staged = (p.H & 3) != 0 ? 1 : env_int("ST_B200_TPE_STAGED", 0);
     s.ctas_per_sm = env_int("ST_B200_TPE_CTAS_PER_SM", 0);
     const int nrec = s.ctas_per_sm > 0 ? 2 : 1;
+    if (tpe_smem_bytes(p, s.epw, s.wpc, s.staged, nrec) > kTpeSmemMax) s.sync = 0;
     while (s.wpc > 1 && tpe_smem_bytes(p, s.epw, s.wpc, s.staged, nrec) > kTpeSmemMax) s.wpc >>= 1;
     while (s.epw > 4 && tpe_smem_bytes(p, s.epw, s.wpc, s.staged, nrec) > kTpeSmemMax) s.epw >>= 1;
     return s;
@@ -968,20 +961,19 @@ static cudaError_t launch_tpe(const Params &p0, cudaStream_t stream)
     const TpeShape s = tpe_shape(p);
     p.tpe_epw = s.epw;
     p.tpe_staged = s.staged;
+    p.tpe_sync = s.sync;
     p.tpe_nrec = s.ctas_per_sm > 0 ? 2 : 1;
-    p.tpe_spec = env_int("ST_B200_TPE_SPEC", 0);  // speculative observation store + fix-up: measured 40-60 % SLOWER (profiles/r2_tpe_speculative_store_ab.txt)
     p.tpe_l2 = env_int("ST_B200_TPE_L2", 1);  // observations / info leave as evict_first streams (measured: -3..5 %)
 #if ST_TPE_TRACE
     static int launch_id = 0;
     p.draw_piece = launch_id++;  // unused by step launches: which of the 8 trace slabs this launch writes
 #endif
-    const bool spec = p.tpe_spec != 0 && p.obs != nullptr && !s.staged && !p.obs_u8;
     if (p.col_words == 1) {
-        if (p.W == 10 && p.H == 20) return spec ? launch_tpe_t<uint32_t, 10, 20, true>(p, s, stream) : launch_tpe_t<uint32_t, 10, 20, false>(p, s, stream);
-        return spec ? launch_tpe_t<uint32_t, 0, 0, true>(p, s, stream) : launch_tpe_t<uint32_t, 0, 0, false>(p, s, stream);
+        if (p.W == 10 && p.H == 20) return launch_tpe_t<uint32_t, 10, 20>(p, s, stream);
+        return launch_tpe_t<uint32_t, 0, 0>(p, s, stream);
     }
-    if (p.W == 20 && p.H == 40) return spec ? launch_tpe_t<unsigned long long, 20, 40, true>(p, s, stream) : launch_tpe_t<unsigned long long, 20, 40, false>(p, s, stream);
-    return spec ? launch_tpe_t<unsigned long long, 0, 0, true>(p, s, stream) : launch_tpe_t<unsigned long long, 0, 0, false>(p, s, stream);
+    if (p.W == 20 && p.H == 40) return launch_tpe_t<unsigned long long, 20, 40>(p, s, stream);
+    return launch_tpe_t<unsigned long long, 0, 0>(p, s, stream);
 }
 
 }  // namespace st

@@ -927,6 +927,7 @@ static cudaError_t launch_t(const Params &p, cudaStream_t stream)
 
 }  // namespace st
 #include "st_kernels_tpe.cuh"
+#include "st_kernels_cols.cuh"
 namespace st {
 
 template <int RPL, int OBS, typename RowT>
@@ -956,15 +957,28 @@ static cudaError_t launch_obs(const Params &p, cudaStream_t stream)
     return launch_mode<2, OBS, unsigned long long>(p, stream);
 }
 
+// Which kernel steps a ram batch: 0 = warp-per-env on row lanes (K1, also every image mode / reset / observe launch),
+// 1 = thread-per-env (K1b), 2 = warp-per-env on column lanes (K1c).  ST_B200_RAM_PATH = warp | thread | cols forces one
+// (where eligible); auto: thread-per-env from tpe_min_envs() envs up, where a warp per env is issue-bound, column lanes
+// below (a warp per env has the shorter critical path there), row lanes for boards wider than 24 columns.
+static int ram_path(const Params &p, int obs_type)
+{
+    const char *path = getenv("ST_B200_RAM_PATH");
+    const char f = path ? path[0] : 'a';
+    const bool tpe_ok = tpe_eligible(p, obs_type), cols_ok = cols_eligible(p, obs_type);
+    if (f == 't') return tpe_ok ? 1 : cols_ok ? 2 : 0;
+    if (f == 'w') return 0;
+    if (f == 'c') return cols_ok ? 2 : 0;
+    if (tpe_ok && p.n >= tpe_min_envs(p)) return 1;
+    return cols_ok ? 2 : 0;
+}
+
 cudaError_t launch_main(const Params &p, int obs_type, cudaStream_t stream)
 {
     if (p.n >= (1ll << 31) - 8) return cudaErrorInvalidValue;
-    if (tpe_eligible(p, obs_type)) {
-        // ST_B200_RAM_PATH = warp | thread | auto (default): thread-per-env from tpe_min_envs() envs up, where the
-        // warp-per-env kernel is issue-bound; below that a warp per env has the shorter critical path
-        const char *path = getenv("ST_B200_RAM_PATH");
-        const bool force_thread = path && path[0] == 't', force_warp = path && path[0] == 'w';
-        if (force_thread || (!force_warp && p.n >= tpe_min_envs(p))) return launch_tpe(p, stream);
+    switch (ram_path(p, obs_type)) {
+    case 1: return launch_tpe(p, stream);
+    case 2: return launch_cols(p, stream);
     }
     switch (obs_type) {
     case 0: return launch_obs<0>(p, stream);
@@ -980,9 +994,10 @@ const char *step_kernel_name(const Params &p, int obs_type)
     Params q = p;
     q.mode = MODE_STEP;
     q.T = 1;
-    const char *path = getenv("ST_B200_RAM_PATH");
-    const bool force_thread = path && path[0] == 't', force_warp = path && path[0] == 'w';
-    if (tpe_eligible(q, obs_type) && (force_thread || (!force_warp && q.n >= tpe_min_envs(q)))) return "st_step_tpe_kernel";
+    switch (ram_path(q, obs_type)) {
+    case 1: return "st_step_tpe_kernel";
+    case 2: return "st_step_cols_kernel";
+    }
     return obs_type == 0 ? "st_main_kernel<ram,STEP>" : obs_type == 1 ? "st_main_kernel<grayscale,STEP>" : "st_main_kernel<rgb,STEP>";
 }
 

@@ -21,7 +21,7 @@ def info_row(info):
             info["holes"], info["deaths"]] + [info["statistics"][n] for n in SHAPE_NAMES]
 
 
-@pytest.fixture(autouse=True, params=["auto", "thread"])
+@pytest.fixture(autouse=True, params=["auto", "thread", "warp"])
 def ram_path(request):
     """Every test runs twice: with the default kernel choice (warp-per-env below 16384 envs) and with the
     thread-per-env ram kernel forced (ST_B200_RAM_PATH is read by the library at every launch)."""

@@ -24,8 +24,10 @@ constexpr int kColsWarpsPerCta = 4;
 // The four cells of a piece, one byte per field (a uniform index here — one piece per warp — so the constant cache
 // broadcasts it, and a byte leaves a word with one PRMT):  i3 = byte k: column offset + 3;  s3 = byte k: row offset + 3;
 // maxj3 = largest row offset + 3.
+//   pat_lo / pat_hi = the piece by COLUMN: a 7-bit pattern per column offset d = i + 3 (bit j + 3 = cell (i, j)),
+//   offsets 0..3 in pat_lo, 4..6 in pat_hi, 7 bits each.
 struct ColsTab {
-    uint32_t i3[28], s3[28], maxj3[28];
+    uint32_t i3[28], s3[28], maxj3[28], pat_lo[28], pat_hi[28];
 };
 constexpr ColsTab make_cols_tab()
 {
@@ -36,6 +38,9 @@ constexpr ColsTab make_cols_tab()
         for (int k = 0; k < 4; ++k) {
             c.i3[s] |= ((lo >> (8 * k)) & 7u) << (8 * k);
             c.s3[s] |= ((lo >> (8 * k + 3)) & 7u) << (8 * k);
+            const uint32_t d = (lo >> (8 * k)) & 7u, j3 = (lo >> (8 * k + 3)) & 7u;
+            if (d < 4) c.pat_lo[s] |= 1u << (7 * d + j3);
+            else c.pat_hi[s] |= 1u << (7 * (d - 4) + j3);
         }
         c.maxj3[s] = (uint32_t)(t.e[s] >> 32) & 15u;
     }
@@ -45,6 +50,7 @@ __constant__ ColsTab c_cols = make_cols_tab();
 
 struct ColsCells {
     int i3[4], s3[4], maxj;  // column offset + 3, row offset + 3 of the four cells; largest row offset
+    uint32_t pat_lo, pat_hi;
 };
 
 __device__ __forceinline__ ColsCells cols_cells(int id, int rot)
@@ -57,6 +63,8 @@ __device__ __forceinline__ ColsCells cols_cells(int id, int rot)
         c.s3[k] = (int)__byte_perm(ws, 0, 0x4440 + k);
     }
     c.maxj = (int)c_cols.maxj3[id * 4 + rot] - 3;
+    c.pat_lo = c_cols.pat_lo[id * 4 + rot];
+    c.pat_hi = c_cols.pat_hi[id * 4 + rot];
     return c;
 }
 
@@ -119,9 +127,10 @@ template <typename ColT>
 __device__ __forceinline__ ColT cols_collisions(ColT col, const ColsCells &c, int x, int X3, int W, int H)
 {
     ColT mine = 0;
+    const int d = X3 - x;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-        if (X3 == x + c.i3[k]) mine |= ColOps<ColT>::by_rows(col, c.s3[k]);  // cells above the board fall off the shift (ref:32-33)
+        if (d == c.i3[k]) mine |= ColOps<ColT>::by_rows(col, c.s3[k]);  // cells above the board fall off the shift (ref:32-33)
     if ((unsigned)(x + 1) > (unsigned)(W + 1)) {  // only an injected anchor: columns beyond the lanes are outside the board too
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -132,18 +141,21 @@ __device__ __forceinline__ ColT cols_collisions(ColT col, const ColsCells &c, in
     return warp_or<ColT>(mine) | (~(ColT)0 << fl);
 }
 
-// This lane's share of the piece at anchor (x, y): its in-board cells in column X3 - 3 (ref:325-326 `0 <= y < height`).
+// This lane's share of the piece at anchor (x, y): its in-board cells in column X3 - 3 (ref:325-326 `0 <= y < height`):
+// the column pattern of offset d = X3 - x, moved to row y.
 template <typename ColT>
 __device__ __forceinline__ ColT cols_piece(const ColsCells &c, int x, int y, int X3, int H)
 {
-    ColT m = 0;
-    const int y3 = y - 3;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int row = y3 + c.s3[k];
-        if (X3 == x + c.i3[k] && (unsigned)row < (unsigned)H) m |= (ColT)1 << row;
-    }
-    return m;
+    const int d = X3 - x;
+    const uint32_t w = d < 4 ? c.pat_lo : c.pat_hi;
+    uint32_t pat = (w >> (7 * (d & 3))) & 127u;
+    if ((unsigned)d > 6u) pat = 0;
+    constexpr int kYMax = sizeof(ColT) == 4 ? 56 : 66;  // an injected anchor far below the floor: every cell drops out
+    y = y > kYMax ? kYMax : y;
+    ColT m;
+    if constexpr (sizeof(ColT) == 4) m = (ColT)(((unsigned long long)pat << y) >> 3);
+    else m = y >= 3 ? ((ColT)pat << (y - 3)) : ((ColT)pat >> (3 - y));
+    return m & (((ColT)1 << H) - 1);
 }
 
 // rows every board column has / rows any board column has / _count_holes (ref:218-220)
@@ -310,6 +322,8 @@ __global__ void __launch_bounds__(32 * kColsWarpsPerCta) st_step_cols_kernel(con
     int ld = uget(sw, lane, 1);
 
     for (int t = 0; t < p.T; ++t) {
+        unsigned int next_u = 6u;  // next step's action: its miss overlaps this step
+        if (t + 1 < p.T) asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(next_u) : "l"(act_p + n));
         // ---- TetrisEngine.step (ref:243-304) ----
         int reward = p.reward_step, done = 0;
         ColT pm = 0;  // this lane's share of the piece the returned state shows (ref:301)
@@ -394,7 +408,7 @@ __global__ void __launch_bounds__(32 * kColsWarpsPerCta) st_step_cols_kernel(con
             info_p += p.info_t_stride;
             obs_p += obs_step;
             term_p += obs_step;
-            action = (int)__reduce_or_sync(FULL, (uint32_t)*act_p);
+            action = (int)__reduce_or_sync(FULL, next_u);
         }
     }
     if (lane < kStateWords) rec_w[lane] = (uint32_t)sw;

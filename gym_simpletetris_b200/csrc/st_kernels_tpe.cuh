@@ -899,9 +899,11 @@ static cudaError_t launch_tpe_t(const Params &p, const TpeShape &s, cudaStream_t
 //   262144     162.6        92.8     56.9     45.4     49.2    |    265.6        171.6    155.9    155.3
 // The per-warp engine chain costs the same for 4 or 32 envs, so mid-size batches get fewer envs per warp (more warps
 // to hide its latency) and large ones more (fewer instructions per env).
-// T steps per launch (records stay in shared memory between steps): 8 envs per group from 6144 envs up
-// (10x20, us per step at T = 32: 8192 envs 2.9 against 3.8 warp-per-env, 32768 envs 6.1 / 13.4, 65536 envs 9.8 / 24.6).
-static long long tpe_min_envs(const Params &p) { return p.T > 1 ? 6144 : 10240; }
+// T steps per launch (records stay in shared memory between steps): 8 envs per group.
+// Below the thresholds the column-lane warp-per-env kernel (st_kernels_cols.cuh) is faster (10x20, us per launch, column
+// lanes / thread-per-env: 8192 envs 6.2 / 8.0, 10240 7.2 / 8.4, 12288 8.2 / 8.5, 16384 ~10.3 / 8.6; at T = 32, us per
+// step: 6144 envs 2.3 / 2.6, 8192 2.8 / 2.75, 12288 4.0 / 3.1).
+static long long tpe_min_envs(const Params &p) { return p.T > 1 ? 8192 : 14336; }
 static int tpe_default_epw(const Params &p)
 {
     if (p.T > 1) return 8;

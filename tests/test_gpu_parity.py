@@ -23,8 +23,9 @@ def info_row(info):
 
 @pytest.fixture(autouse=True, params=["auto", "thread", "warp"])
 def ram_path(request):
-    """Every test runs twice: with the default kernel choice (warp-per-env below 16384 envs) and with the
-    thread-per-env ram kernel forced (ST_B200_RAM_PATH is read by the library at every launch)."""
+    """Every test runs twice: with the default kernel choice (column-lane warp-per-env kernel below 14336 envs), with the
+    thread-per-env ram kernel forced and with the row-lane warp-per-env kernel forced (ST_B200_RAM_PATH is read by the
+    library at every launch)."""
     import os
 
     old = os.environ.get("ST_B200_RAM_PATH")

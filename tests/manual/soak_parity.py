@@ -1,5 +1,6 @@
-"""Long randomized parity soak: VecEnv (both ram kernels, image modes) vs the C oracle on the same Philox streams.
-Not part of the test suite (minutes of CPU time); run on the GPU box:  python tests/manual/soak_parity.py"""
+"""Long randomized parity soak: VecEnv (all three ram kernels, image modes) vs the C oracle on the same Philox streams.
+Not part of the test suite (minutes of CPU time); run on the GPU box:  python tests/manual/soak_parity.py [paths]
+(paths: comma-separated subset of warp,cols,thread — default all; "cols" alone also skips the image configs)"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests"))
@@ -10,13 +11,16 @@ from oracle.oracle import rollout
 from _cases import CASES
 
 INFO13 = [2, 0, 3, 4, 5, 7] + list(range(8, 15))
+RAM_PATHS = sys.argv[1].split(",") if len(sys.argv) > 1 else ["warp", "cols", "thread"]
 rs = np.random.RandomState(2026)
 total = 0
 t0 = time.time()
 for name, kw in CASES.items():
     image = kw.get("obs_type", "ram") != "ram"
     n, T = (96, 600) if image else (1500, 2500)
-    for path in (["auto"] if image else ["warp", "thread"]):
+    if image and len(sys.argv) > 1:
+        continue
+    for path in (["auto"] if image else RAM_PATHS):
         os.environ["ST_B200_RAM_PATH"] = path
         # biased action mix: more hard drops and rotations than uniform, to reach deeper stacks and more clears
         acts = rs.choice(7, size=(T, n), p=[0.16, 0.16, 0.22, 0.08, 0.14, 0.14, 0.10]).astype(np.uint8)

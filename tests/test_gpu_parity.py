@@ -107,6 +107,15 @@ EXTRA_CASES = {
     "w26h40_wide_tall": dict(width=26, height=40, lock_delay=2, step_reset=True, penalise_height_increase=True),
     "w25h8_wide_low": dict(width=25, height=8, advanced_clears=True),
     "w5h60_narrow_tall": dict(width=5, height=60, high_scoring=True, penalise_holes_increase=True),
+    # edges of the column-lane warp kernel (st_kernels_cols.cuh): 24 columns is its widest board (lanes 4..27 + walls),
+    # 12x20 fills both precomputed float4 slots of a lane (60 of 64), 13x20 falls to its generic observation loop,
+    # 4x40 takes the precomputed slots with 64-bit columns, 6x63 the element-wise loop with 64-bit columns
+    "w24h20_cols_widest": dict(width=24, height=20, reward_step=True, penalise_height_increase=True),
+    "w24h40_cols_widest_tall": dict(width=24, height=40, lock_delay=1, penalise_holes=True),
+    "w12h20_two_slots": dict(width=12, height=20, advanced_clears=True),
+    "w13h20_generic_obs": dict(width=13, height=20, high_scoring=True, step_reset=True, lock_delay=2),
+    "w4h40_tall_fast_obs": dict(width=4, height=40, penalise_holes_increase=True, reward_step=True),
+    "w6h63_tallest": dict(width=6, height=63, penalise_height=True),
 }
 
 

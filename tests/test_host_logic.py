@@ -37,8 +37,10 @@ def test_config_marshalling_round_trip():
     assert L.st_state_stride(C.byref(cfg)) == 60 + 24 * 2
     assert L.st_step_kernel_name(C.byref(cfg), 4096).decode().startswith("st_main_kernel<grayscale")
     ram = native.make_config(**{**{f[0]: getattr(cfg, f[0]) for f in cfg._fields_}, "obs_type": "ram"})
-    assert L.st_step_kernel_name(C.byref(ram), 4096).decode() == "st_main_kernel<ram,STEP>"
-    assert L.st_step_kernel_name(C.byref(ram), 1 << 20).decode() == "st_step_tpe_kernel"
+    assert L.st_step_kernel_name(C.byref(ram), 4096).decode() == "st_step_cols_kernel"   # column lanes: small batches
+    assert L.st_step_kernel_name(C.byref(ram), 1 << 20).decode() == "st_step_tpe_kernel"  # thread per env: large ones
+    wide = native.make_config(**{**{f[0]: getattr(ram, f[0]) for f in ram._fields_}, "width": 28})
+    assert L.st_step_kernel_name(C.byref(wide), 4096).decode() == "st_main_kernel<ram,STEP>"  # > 24 columns: row lanes
 
 
 def test_info_columns_match_header_order():

@@ -39,7 +39,7 @@ def test_config_marshalling_round_trip():
     ram = native.make_config(**{**{f[0]: getattr(cfg, f[0]) for f in cfg._fields_}, "obs_type": "ram"})
     assert L.st_step_kernel_name(C.byref(ram), 4096).decode() == "st_step_cols_kernel"   # column lanes: small batches
     assert L.st_step_kernel_name(C.byref(ram), 1 << 20).decode() == "st_step_tpe_kernel"  # thread per env: large ones
-    wide = native.make_config(**{**{f[0]: getattr(ram, f[0]) for f in ram._fields_}, "width": 28})
+    wide = native.make_config(**{**{f[0]: getattr(ram, f[0]) for f in ram._fields_}, "obs_type": "ram", "width": 28})
     assert L.st_step_kernel_name(C.byref(wide), 4096).decode() == "st_main_kernel<ram,STEP>"  # > 24 columns: row lanes
 
 

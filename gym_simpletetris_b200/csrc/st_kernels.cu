@@ -14,7 +14,9 @@
 // Observations: ram is expanded by the env's own warp from a smem staging row with 16-byte stores;
 // 84x84 images are written by the whole CTA (8 envs) with every thread owning a fixed 16-byte column
 // slot, so a warp store covers 512 contiguous bytes; rgb leaves through TMA bulk stores from a shared-memory ring.
-// Large ram batches take the thread-per-env kernel of st_kernels_tpe.cuh instead (see launch_main).
+// Ram batches are stepped by two other kernels since round 2 (see ram_path / launch_main): small ones by the
+// column-lane warp-per-env kernel of st_kernels_cols.cuh, large ones by the thread-per-env kernel of st_kernels_tpe.cuh;
+// this kernel keeps the image modes, reset / observe launches and ram boards wider than 24 columns.
 //
 // Compile-time tuning knobs (defaults are the measured best on B200; DESIGN.md section 6 lists what was tried).
 #include "st_internal.h"

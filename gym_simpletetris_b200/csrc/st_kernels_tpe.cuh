@@ -1,13 +1,11 @@
-// K1b — thread-per-env ram step on COLUMN bitboards, observations staged in shared memory and sent out with TMA
-// bulk stores (included by st_kernels.cu).
+// K1b — thread-per-env ram step on COLUMN bitboards (included by st_kernels.cu).
 //
-// The warp-per-env kernel (K1) spends ~400 warp-instructions per env-step: ideal for small batches, where the
-// machine is latency-bound and a whole warp per env keeps every rare branch uniform, but issue-bound from
-// ~16k envs up.  Here one THREAD steps one env and the warp does the memory work cooperatively, for one GROUP of
-// `epw` consecutive envs at a time (a warp walks over several groups when the grid is capped):
-//   1. the group's env records (contiguous in HBM) arrive in shared memory through cp.async (LDGSTS), the next
-//      group's records are already in flight while this one is stepped; the record pitch in smem is odd, so lane r
-//      touching word c of ITS record is conflict-free;
+// A warp per env costs 270-580 warp-instructions per env-step: ideal for small batches, where the machine is
+// latency-bound and a whole warp per env keeps every rare branch uniform, but issue-bound from ~14k envs up.  Here one
+// THREAD steps one env and the warp does the memory work cooperatively, for one GROUP of `epw` consecutive envs at a
+// time (a warp walks over several groups when the grid is capped):
+//   1. the group's env records (contiguous in HBM) arrive in shared memory through cp.async (LDGSTS); the record pitch
+//      in smem is odd, so lane r touching word c of ITS record is conflict-free;
 //   2. each lane runs TetrisEngine.step (ref:243-304) on its record in smem.  The record holds the board as one
 //      word per COLUMN (bit y of column x = cell (x, y)), which is what makes the per-thread engine short:
 //        * a piece is four cells (i, j); the collision answer for EVERY anchor height at once is the OR over the
@@ -16,14 +14,13 @@
 //          soft drop, hard drop (one ctz — no search loop), gravity and the grounded test read bits of that mask;
 //        * full rows are the AND of all columns, holes are H - top - popc per column, height is popc of the OR;
 //          a cleared row is squeezed out of every column with three logic ops;
-//   3. info / reward / done go out coalesced, auto-reset envs are cleared, every other lane ORs its piece
-//      into its smem columns (the reference's _set_piece(True), ref:301);
-//   4. the warp expands the group's boards into float32 [W][H] — the observation is column-major like the record:
-//      one lane per (env, column), four cells = four adjacent bits = one 16-byte table entry — into a warp-private
-//      staging block in shared memory, and ONE cp.async.bulk (TMA) store sends the block (the group's
-//      observations are contiguous in HBM) on its way; the warp does not wait for it: the block is only
-//      needed again after the next group's records were stepped;
-//   5. lanes erase their piece again (ref:303) and the records are stored back, coalesced.
+//   3. reward / done go out, auto-reset envs are cleared, every other lane ORs its piece into its smem columns (the
+//      reference's _set_piece(True), ref:301);
+//   4. the warp expands the group's boards into float32 [W][H] — the observation is column-major like the record —
+//      with direct 16-byte stores, 512 contiguous bytes per warp instruction (tpe_obs_direct); boards whose height is
+//      not a multiple of 4 go through two chunk buffers in shared memory and cp.async.bulk (TMA) stores instead;
+//   5. info, then lanes erase their piece again (ref:303) and the records are stored back, coalesced.
+// DESIGN.md section 3 (K1b) has the measured phase timeline and what was tried against it.
 #pragma once
 
 namespace st {
@@ -828,6 +825,12 @@ __global__ void __launch_bounds__(32 * kTpeMaxWarps, ST_TPE_MINBLOCKS) st_step_t
     if (errbits && p.err && lane == 0) atomicOr(p.err, errbits);
 }
 
+static int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
 // Launch shape of the thread-per-env kernel: envs per group, warps per CTA, grid cap (CTAs per SM; 0 = one group per warp).
 struct TpeShape {
     int epw, wpc, ctas_per_sm, staged, sync;
@@ -859,7 +862,9 @@ static cudaError_t launch_tpe_t(const Params &p, const TpeShape &s, cudaStream_t
 {
     const long long ngroups = (p.n + s.epw - 1) / s.epw;
     long long nctas = (ngroups + s.wpc - 1) / s.wpc;
-    const size_t smem = tpe_smem_bytes(p, s.epw, s.wpc, s.staged, p.tpe_nrec);
+    // ST_B200_TPE_SMEM_PAD: experiment knob, unused dynamic shared memory that caps the resident CTAs per SM (waves)
+    size_t smem = tpe_smem_bytes(p, s.epw, s.wpc, s.staged, p.tpe_nrec) + (size_t)env_int("ST_B200_TPE_SMEM_PAD", 0);
+    if (smem > kTpeSmemMax) smem = kTpeSmemMax;
     static const bool pdl = getenv("ST_B200_NO_PDL") == nullptr;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -909,12 +914,6 @@ static int tpe_default_epw(const Params &p)
     if (p.T > 1) return 8;
     if (p.H <= 31) return p.n < 20480 ? 4 : p.n < 57344 ? 8 : 16;
     return p.n < 24576 ? 4 : 8;
-}
-
-static int env_int(const char *name, int dflt)
-{
-    const char *v = getenv(name);
-    return v ? atoi(v) : dflt;
 }
 
 static TpeShape tpe_shape(const Params &p)

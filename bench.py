@@ -350,8 +350,10 @@ def write_only_ceiling_gbs():
     return round(best, 1)
 
 
-def pcie_d2h_peak_gbs():
-    """GB/s of a plain 256 MiB device -> pinned-host cudaMemcpyAsync on this GPU's link (best of 5): the ceiling of `e2e`."""
+def pcie_d2h_peak_gbs(dist=None):
+    """GB/s of a plain 256 MiB device -> pinned-host cudaMemcpyAsync on this GPU's link (best of 5): the ceiling of `e2e`.
+    With `dist` (N > 1, called by every rank): all ranks copy AT THE SAME TIME — what the host's memory system gives
+    each link when all of them are busy, which is the ceiling of the N-GPU `e2e`; returns the minimum over ranks."""
     import torch
 
     d = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -359,12 +361,19 @@ def pcie_d2h_peak_gbs():
     best = 0.0
     for i in range(6):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if dist is not None:
+            torch.cuda.synchronize()
+            dist.barrier()
         a.record()
         h.copy_(d, non_blocking=True)
         b.record()
         torch.cuda.synchronize()
         if i >= 1:
             best = max(best, d.numel() / (a.elapsed_time(b) * 1e-3) / 1e9)
+    if dist is not None:
+        t = torch.tensor([best], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        best = float(t.item())
     del d, h
     torch.cuda.empty_cache()
     return round(best, 2)
@@ -616,7 +625,10 @@ def main():
             r["scaling"] = "strong"
             modes["C4_strong"] = r
     fill_gbs = write_only_ceiling_gbs() if rank == 0 else None
-    pcie = pcie_d2h_peak_gbs() if (rank == 0 and not args.no_e2e) else None
+    pcie_all = pcie_d2h_peak_gbs(dist) if (world > 1 and not args.no_e2e) else None  # every rank at the same time
+    if world > 1:
+        dist.barrier()
+    pcie = pcie_d2h_peak_gbs() if (rank == 0 and not args.no_e2e) else None         # rank 0 alone
     clocks = sampler.stop()
     if world > 1:
         dist.barrier()
@@ -631,6 +643,9 @@ def main():
     if e2e is not None:
         e2e["pcie_d2h_peak_gbs"] = pcie
         e2e["pcie_frac"] = round(e2e["d2h_gbs_per_gpu"] / pcie, 3) if pcie else None
+        if pcie_all:  # N > 1: the host delivers less per link when all links copy at once; that is the ceiling here
+            e2e["pcie_d2h_all_ranks_busy_gbs"] = pcie_all
+            e2e["pcie_frac_all_ranks_busy"] = round(e2e["d2h_gbs_per_gpu"] / pcie_all, 3)
     line = {
         "metric": "env-steps/sec", "value": head["value"], "unit": "env-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,

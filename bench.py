@@ -352,8 +352,9 @@ def write_only_ceiling_gbs():
 
 def pcie_d2h_peak_gbs(dist=None):
     """GB/s of a plain 256 MiB device -> pinned-host cudaMemcpyAsync on this GPU's link (best of 5): the ceiling of `e2e`.
-    With `dist` (N > 1, called by every rank): all ranks copy AT THE SAME TIME — what the host's memory system gives
-    each link when all of them are busy, which is the ceiling of the N-GPU `e2e`; returns the minimum over ranks."""
+    With `dist` (N > 1, called by every rank): all ranks copy AT THE SAME TIME and the rates of one round are summed —
+    what the host's memory system delivers when every link is busy; returns the best round's sum / N, the mean per
+    link, which is the ceiling of the N-GPU `e2e`."""
     import torch
 
     d = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -368,12 +369,13 @@ def pcie_d2h_peak_gbs(dist=None):
         h.copy_(d, non_blocking=True)
         b.record()
         torch.cuda.synchronize()
+        rate = d.numel() / (a.elapsed_time(b) * 1e-3) / 1e9
+        if dist is not None:
+            t = torch.tensor([rate], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            rate = float(t.item()) / dist.get_world_size()
         if i >= 1:
-            best = max(best, d.numel() / (a.elapsed_time(b) * 1e-3) / 1e9)
-    if dist is not None:
-        t = torch.tensor([best], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MIN)
-        best = float(t.item())
+            best = max(best, rate)
     del d, h
     torch.cuda.empty_cache()
     return round(best, 2)

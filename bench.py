@@ -176,6 +176,31 @@ def ncu_traffic_bytes(name):
     return (int(tot) if tot else None), os.path.relpath(files[-1], ROOT)
 
 
+def ncu_issue_metrics(name):
+    """Issue-side figures of the same ncu capture (ram modes are judged by instruction issue, not bytes):
+    % of cycles a scheduler issued while the SM was active, ALU / LSU pipe utilisation and dynamic warp-instructions
+    of ONE launch.  None when the round has no profile of this workload."""
+    import glob
+    import re
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"r*_{name}_step_kernel_ncu_full.txt")),
+                   key=lambda f: int(re.search(r"r(\d+)_", os.path.basename(f)).group(1)))
+    if not files:
+        return None
+    want = {"smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active_pct",
+            "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active": "alu_pipe_pct",
+            "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active": "lsu_pipe_pct",
+            "smsp__inst_executed.sum": "warp_instructions_per_launch"}
+    out = {}
+    with open(files[-1]) as f:
+        for ln in f:
+            parts = ln.split()
+            if len(parts) >= 2 and parts[0] in want and want[parts[0]] not in out:
+                out[want[parts[0]]] = float(parts[1])
+    out["source"] = os.path.relpath(files[-1], ROOT)
+    return out if len(out) > 1 else None
+
+
 def replica_plan(steps, per_step_bytes):
     """(R, L): R replicas of the batch, and a captured sequence of L launches (a multiple of `steps`, R divides L,
     launch u runs on replica u % R) so that every replica is revisited only after R - 1 other launches, i.e. after
@@ -326,6 +351,13 @@ def time_workload(name, steps, warmup, rank, world, dist, burn_in=200, T=1, n_ov
                      "algorithmic_bytes_per_env_step": B, "env_steps_per_launch": n * T,
                      "avg_launch_ms": round(kernel_ms, 6)},
     }
+    issue = ncu_issue_metrics(tag or name) if not image else None
+    if issue:  # ram modes: the north star asks for integer-pipe / issue utilisation beside the byte roofline
+        if "warp_instructions_per_launch" in issue:
+            issue["warp_instructions_per_env_step"] = round(issue["warp_instructions_per_launch"] / (n * T), 1)
+        issue["note"] = ("ncu --set full capture of one launch (cold, serialised): issue slots busy while the SM is active; "
+                         "ram modes are bound by instruction issue / latency, not by bytes")
+        res["roofline"]["issue"] = issue
     del envs, actions, graphs, roll
     torch.cuda.empty_cache()
     return res

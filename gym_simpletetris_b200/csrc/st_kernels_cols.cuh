@@ -10,9 +10,12 @@
 //   * lock: each lane ORs its share of the piece into its column; full rows = REDUX.AND, rows with any cell = REDUX.OR,
 //     holes = REDUX.ADD of (H - top - popc) per lane; a cleared row is squeezed out of every column in parallel;
 //   * the scalar part of the record (15 words) sits one word per lane, as in the row kernel (K1).
+//   * scalars are broadcast with REDUX, not SHFL: a REDUX result is a uniform register, so the compiler knows every
+//     branch on it is warp-uniform (a shuffle result is "divergent" to it and every `if` gets a convergence barrier).
 // Control flow is uniform per warp (one env), so the lock / spawn / reset branches cost nothing when they are not
-// taken.  ~190 warp-instructions per env-step against ~580 for K1, which pays a column<->row transpose at both ends
-// of every step since the record went column-major; same reward table, Philox stream and error flags.
+// taken.  Measured (ncu, 4096 envs of 10x20): 270 warp-instructions per env-step inside a T-step launch, 400 in a
+// one-step launch, against 425 / 580 for K1, which pays a column<->row transpose at both ends of every step since the
+// record went column-major; same reward table, Philox stream and error flags.
 #pragma once
 
 namespace st {

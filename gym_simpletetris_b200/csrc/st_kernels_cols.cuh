@@ -22,7 +22,10 @@ namespace st {
 
 constexpr int kColsLaneOff = 4;   // lane of board column 0: a candidate anchor at x = -1 with a cell at i = -3 is lane 0
 constexpr int kColsMaxW = 24;     // ... and x = W with i = +3 is lane W + 7 <= 31
-constexpr int kColsWarpsPerCta = 4;
+#ifndef ST_COLS_WARPS
+#define ST_COLS_WARPS 4  // warps (= envs) per CTA: tuning knob
+#endif
+constexpr int kColsWarpsPerCta = ST_COLS_WARPS;
 
 // The four cells of a piece, one byte per field (a uniform index here — one piece per warp — so the constant cache
 // broadcasts it, and a byte leaves a word with one PRMT):  i3 = byte k: column offset + 3;  s3 = byte k: row offset + 3;
@@ -267,8 +270,12 @@ __device__ __forceinline__ void cols_write_ram(ColT shown, void *out, const floa
     }
 }
 
-template <typename ColT>
-__global__ void __launch_bounds__(32 * kColsWarpsPerCta) st_step_cols_kernel(const __grid_constant__ Params p)
+// MINB = the min-blocks hint of __launch_bounds__, i.e. the register budget: the kernel is latency-bound, so the build
+// with the most registers (most loads and table reads hoisted) is the fastest AS LONG AS the whole batch is resident in
+// one wave; launch_cols picks the instantiation by occupancy (measured on B200, 10x20, us per launch, 72 / 63 / 53
+// registers: 2048 envs 3.26 / 3.73 / 4.19, 4096 envs 3.89 / 4.28 / 4.55, 5120 envs 5.06 / 4.98 / 4.46).
+template <typename ColT, int MINB>
+__global__ void __launch_bounds__(32 * kColsWarpsPerCta, MINB) st_step_cols_kernel(const __grid_constant__ Params p)
 {
     __shared__ __align__(16) float4 s_lut[16];
     constexpr int CW = ColOps<ColT>::kWords;
@@ -432,6 +439,35 @@ static bool cols_eligible(const Params &p, int obs_type)
     return obs_type == 0 && p.mode == MODE_STEP && p.n > 0 && p.W <= kColsMaxW && p.H <= 63;
 }
 
+// Envs one wave of an instantiation holds on this device (resident CTAs per SM x SMs x envs per CTA), cached.
+template <typename ColT, int MINB>
+static long long cols_wave_envs()
+{
+    static long long cap[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 0;
+    if (!cap[dev]) {
+        int ctas = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, st_step_cols_kernel<ColT, MINB>, 32 * kColsWarpsPerCta, 0) != cudaSuccess)
+            ctas = 0;
+        cap[dev] = (long long)ctas * tpe_sm_count() * kColsWarpsPerCta;
+        if (!cap[dev]) cap[dev] = -1;
+    }
+    return cap[dev] > 0 ? cap[dev] : 0;
+}
+
+template <typename ColT>
+static cudaError_t launch_cols_t(const Params &p, cudaLaunchConfig_t &cfg)
+{
+    // register budgets, richest first: 1 (no cap: ~72 registers), 7 (<= 73), 0 (the compiler's own choice: ~53)
+    const int force = env_int("ST_B200_COLS_MINB", -1);  // experiment knob, read at every launch like ST_B200_RAM_PATH
+    const int pick = force >= 0 ? force : p.n <= cols_wave_envs<ColT, 1>() ? 1 : p.n <= cols_wave_envs<ColT, 7>() ? 7 : 0;
+    if (pick == 1) return cudaLaunchKernelEx(&cfg, st_step_cols_kernel<ColT, 1>, p);
+    if (pick == 7) return cudaLaunchKernelEx(&cfg, st_step_cols_kernel<ColT, 7>, p);
+    return cudaLaunchKernelEx(&cfg, st_step_cols_kernel<ColT, 0>, p);
+}
+
 static cudaError_t launch_cols(const Params &p, cudaStream_t stream)
 {
     static const bool pdl = getenv("ST_B200_NO_PDL") == nullptr;
@@ -445,8 +481,8 @@ static cudaError_t launch_cols(const Params &p, cudaStream_t stream)
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     count_launch();
-    if (p.col_words == 1) return cudaLaunchKernelEx(&cfg, st_step_cols_kernel<uint32_t>, p);
-    return cudaLaunchKernelEx(&cfg, st_step_cols_kernel<unsigned long long>, p);
+    if (p.col_words == 1) return launch_cols_t<uint32_t>(p, cfg);
+    return launch_cols_t<unsigned long long>(p, cfg);
 }
 
 }  // namespace st

@@ -526,7 +526,7 @@ __device__ __forceinline__ void tpe_obs_direct(const uint32_t *recs, unsigned ch
 // WCT / HCT: board size known at compile time (0 = taken from Params): the column loops unroll and the divisions by
 // W, H / 4 fold into constants for the boards every BASELINE.json workload uses.
 template <typename ColT, int WCT, int HCT>
-__global__ void __launch_bounds__(32 * kTpeMaxWarps, ST_TPE_MINBLOCKS) st_step_tpe_kernel(const __grid_constant__ Params p)
+__device__ __forceinline__ void tpe_step_body(const Params &p)
 {
     extern __shared__ __align__(128) uint32_t s_dyn[];
     __shared__ unsigned long long s_cells[56];  // CellTab: e[28], then c[28]
@@ -825,6 +825,26 @@ __global__ void __launch_bounds__(32 * kTpeMaxWarps, ST_TPE_MINBLOCKS) st_step_t
     if (errbits && p.err && lane == 0) atomicOr(p.err, errbits);
 }
 
+// Two entry points of the same body.  The default build is capped at 64 registers (32 resident warps per SM: what
+// multi-wave batches, T-step launches and the 64-bit-column boards want).  The second one gets 72 registers — 7 CTAs of
+// 4 warps per SM, i.e. the 28 warps per SM of a one-wave batch with nothing to spare: measured on B200, one-step
+// launches of 10x20 boards, us per launch, 64 / 72 registers: 16384 envs 8.76 / 7.92, 32768 envs 10.18 / 9.50,
+// 65536 envs 14.61 / 14.01, 262144 envs 44.0 / 43.7; 20x40 boards: 16384 envs 13.9 / 13.0, 32768 envs 23.0 / 22.2, but
+// 65536 envs 39.5 / 40.5, and T = 32: 9.46 / 9.56 — those keep 64.
+template <typename ColT, int WCT, int HCT>
+__global__ void __launch_bounds__(32 * kTpeMaxWarps, ST_TPE_MINBLOCKS) st_step_tpe_kernel(const __grid_constant__ Params p)
+{
+    tpe_step_body<ColT, WCT, HCT>(p);
+}
+#ifndef ST_TPE_R72_NREG
+#define ST_TPE_R72_NREG 72  // experiment knob
+#endif
+template <typename ColT, int WCT, int HCT>
+__global__ void __maxnreg__(ST_TPE_R72_NREG) st_step_tpe_kernel_r72(const __grid_constant__ Params p)
+{
+    tpe_step_body<ColT, WCT, HCT>(p);
+}
+
 static int env_int(const char *name, int dflt)
 {
     const char *v = getenv(name);
@@ -868,10 +888,16 @@ static cudaError_t launch_tpe_t(const Params &p, const TpeShape &s, cudaStream_t
     static const bool pdl = getenv("ST_B200_NO_PDL") == nullptr;
     int dev = 0;
     cudaGetDevice(&dev);
+    // 72-register entry point: one-step launches on 32-bit columns, CTAs of at most 28 warps (ST_B200_TPE_R72 = 0 / 1 forces)
+    const int r72_knob = env_int("ST_B200_TPE_R72", -1);
+    const bool r72 = s.wpc <= 28 && (r72_knob >= 0 ? r72_knob != 0 : (p.T == 1 && (sizeof(ColT) == 4 || p.n < 49152)));
+    const auto kernel = r72 ? st_step_tpe_kernel_r72<ColT, WCT, HCT> : st_step_tpe_kernel<ColT, WCT, HCT>;
     static bool attr_set[64] = {};
     static int n_sm[64] = {};
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(st_step_tpe_kernel<ColT, WCT, HCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTpeSmemMax);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(st_step_tpe_kernel_r72<ColT, WCT, HCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTpeSmemMax);
         if (e != cudaSuccess) return e;
         cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev);
         attr_set[dev] = true;
@@ -891,28 +917,30 @@ static cudaError_t launch_tpe_t(const Params &p, const TpeShape &s, cudaStream_t
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     count_launch();
-    return cudaLaunchKernelEx(&cfg, st_step_tpe_kernel<ColT, WCT, HCT>, p);
+    return cudaLaunchKernelEx(&cfg, kernel, p);
 }
 
-// Which batches take this kernel and with how many envs per group: measured on B200 (tools/knob_sweep.py, profiles/
-// r2_ram_path_sweep_after.txt; us per single-step launch, 10x20 boards / 20 wide x 40 high boards):
-//   n        warp-per-env   epw 4    epw 8    epw 16   epw 32  |  warp-per-env   epw 4    epw 8    epw 16
-//   8192         7.8         8.0      9.1      9.5      8.1    |     12.0         12.3     16.8     14.7
-//   16384       13.1         8.6      9.2     11.8      9.5    |     20.2         14.3     18.4     25.3
-//   32768       23.3        14.4     10.2     13.4     17.3    |     36.8         25.0     23.2     31.8
-//   65536       43.1        25.5     16.4     15.0     18.8    |     69.4         42.2     38.6     41.7
-//   262144     162.6        92.8     56.9     45.4     49.2    |    265.6        171.6    155.9    155.3
+// Which batches take this kernel and with how many envs per group: measured on B200 (tools/knob_sweep.py; us per
+// one-step launch, 10x20 boards, 72-register entry point; cols = the column-lane warp-per-env kernel):
+//   n         cols    epw 4    epw 8    epw 16         n         epw 4    epw 8    epw 16
+//   8192      6.18     5.98     7.97     9.27         32768      14.11     9.55    11.81
+//   10240     7.22     7.71     8.35     9.43         40960      16.92    12.33    13.10
+//   12288     8.23     7.83     8.71    10.22         49152      20.02    13.52    13.43
+//   14336     9.22     7.97     8.61    10.69         57344      22.92    15.03    14.57
+//   16384    ~10.3     7.93     7.50    10.45         65536      25.56    16.20    14.01
+//   24576       -     11.26     9.17    11.91        131072      49.54    30.82    24.82
 // The per-warp engine chain costs the same for 4 or 32 envs, so mid-size batches get fewer envs per warp (more warps
-// to hide its latency) and large ones more (fewer instructions per env).
+// to hide its latency) and large ones more (fewer instructions per env); a group count just under one wave (4144 warps
+// at 7 CTAs per SM) is the sweet spot, a little over it the worst case.
+// 20 wide x 40 high boards: 4 envs per group below 24576 envs (16384 envs: 13.0 against 15.2 us), 8 above.
 // T steps per launch (records stay in shared memory between steps): 8 envs per group.
-// Below the thresholds the column-lane warp-per-env kernel (st_kernels_cols.cuh) is faster (10x20, us per launch, column
-// lanes / thread-per-env: 8192 envs 6.2 / 8.0, 10240 7.2 / 8.4, 12288 8.2 / 8.5, 16384 ~10.3 / 8.6; at T = 32, us per
-// step: 6144 envs 2.3 / 2.6, 8192 2.8 / 2.75, 12288 4.0 / 3.1).
-static long long tpe_min_envs(const Params &p) { return p.T > 1 ? 8192 : 14336; }
+// Below the thresholds the column-lane warp-per-env kernel (st_kernels_cols.cuh) is as fast or faster (table above; at
+// T = 32, us per step, column lanes / thread-per-env: 6144 envs 2.3 / 2.6, 8192 2.8 / 2.75, 12288 4.0 / 3.1).
+static long long tpe_min_envs(const Params &p) { return p.T > 1 ? 8192 : 11264; }
 static int tpe_default_epw(const Params &p)
 {
     if (p.T > 1) return 8;
-    if (p.H <= 31) return p.n < 20480 ? 4 : p.n < 57344 ? 8 : 16;
+    if (p.H <= 31) return p.n < 16384 ? 4 : p.n < 49152 ? 8 : 16;
     return p.n < 24576 ? 4 : 8;
 }
 

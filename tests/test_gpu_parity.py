@@ -23,7 +23,7 @@ def info_row(info):
 
 @pytest.fixture(autouse=True, params=["auto", "thread", "warp"])
 def ram_path(request):
-    """Every test runs twice: with the default kernel choice (column-lane warp-per-env kernel below 14336 envs), with the
+    """Every test runs twice: with the default kernel choice (column-lane warp-per-env kernel below 11264 envs), with the
     thread-per-env ram kernel forced and with the row-lane warp-per-env kernel forced (ST_B200_RAM_PATH is read by the
     library at every launch)."""
     import os

@@ -77,3 +77,16 @@ def test_python_reference_timing_runs():
     r1, n1 = single_env_rate(dict(reward_step=True, advanced_clears=True), budget_s=0.6)
     rv, nv = per_core_vector_rate(dict(reward_step=True, advanced_clears=True), workers=2, budget_s=0.5)
     assert r1 > 1000 and n1 > 0 and rv > 1000 and nv > 0
+
+
+def test_profile_readers_find_the_round_profiles():
+    """roofline.traffic and roofline.issue come from the committed ncu summaries, never from constants in bench.py."""
+    import bench
+
+    for name in ("C2", "C3", "C4", "C5a", "C5b", "C2_T32", "C3_T32"):
+        traffic, src = bench.ncu_traffic_bytes(name)
+        assert traffic and traffic > 0 and src.startswith("profiles/r"), name
+        issue = bench.ncu_issue_metrics(name)
+        assert issue and 0 < issue["issue_active_pct"] <= 100 and issue["warp_instructions_per_launch"] > 0, name
+    assert bench.ncu_traffic_bytes("no_such_workload") == (None, None)
+    assert bench.ncu_issue_metrics("no_such_workload") is None
